@@ -1,0 +1,193 @@
+"""ctypes binding of libadamvs_b200.so (the C ABI in include/adamvs_b200.h) for torch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every op below marshals
+``tensor.data_ptr()`` + shapes + ``torch.cuda.current_stream()`` into one C call.  There is no CPU path
+and no torch fallback: without the compiled library or a CUDA tensor these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadamvs_b200.so")
+
+HYP_PLANES, HYP_PER_PIXEL = 0, 1
+EPS_NUMERATOR, EPS_DENOMINATOR = 0, 1
+PROB_SOFTMAX, PROB_EXP_EPS = 0, 1
+INTERVAL_LAST_COLUMN, INTERVAL_FROM_RANGE = 0, 1
+
+EXPORTS = (
+    "adamvs_abi_version", "adamvs_cascade_prepare", "adamvs_pair_score_f32", "adamvs_resize_bilinear_f32",
+    "adamvs_fused_volume_f32", "adamvs_regnet_red_workspace_floats", "adamvs_regnet_red_f32",
+    "adamvs_softmax_regress_f32",
+)
+
+
+class RegnetWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "conv1_w", "gates1_w", "gates1_b", "cand1_w", "cand1_b", "conv2_w", "gates2_w", "gates2_b",
+        "cand2_w", "cand2_b", "up1_w", "up1_b", "out_w", "out_b")]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) the in-tree shared library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m adamvs_b200.build` "
+                "(adamvs_b200 has no CPU or torch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        L.adamvs_abi_version.restype = ci
+        L.adamvs_cascade_prepare.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(ci),
+                                             ctypes.POINTER(ctypes.c_double), vp, vp, vp]
+        L.adamvs_pair_score_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_resize_bilinear_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_fused_volume_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_regnet_red_workspace_floats.argtypes = [ci, ci, ci, ci, ci, ci]
+        L.adamvs_regnet_red_workspace_floats.restype = cs
+        L.adamvs_regnet_red_f32.argtypes = [vp, ctypes.POINTER(RegnetWeights), ci, vp, ci, vp, ci, ci, vp, cs,
+                                            vp, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_softmax_regress_f32.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]
+        for name in EXPORTS:
+            if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats"):
+                getattr(L, name).restype = ci
+        if L.adamvs_abi_version() != 1:
+            raise RuntimeError("libadamvs_b200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+class AdamvsError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise AdamvsError(f"{what}: argument error {rc} (ADAMVS_EINVAL=-1, ADAMVS_ENOSPACE=-2)")
+    raise AdamvsError(f"{what}: CUDA error {rc}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise AdamvsError(f"{name} must be a CUDA tensor (adamvs_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise AdamvsError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Hyp:
+    """Depth-hypothesis source for one stage (reference get_depth_range_samples, module.py:646-663)."""
+
+    def __init__(self, mode: int, src: torch.Tensor, half_range: Optional[torch.Tensor] = None):
+        self.mode = mode
+        self.src = _f32c(src, "hyp_src")
+        self.ncol = int(src.shape[1]) if mode == HYP_PLANES else 0
+        self.half_range = half_range
+
+    def args(self):
+        return self.mode, _p(self.src), self.ncol, _p(self.half_range)
+
+
+def cascade_prepare(proj: Sequence[torch.Tensor], depth_values: torch.Tensor, interval_mode: int, num_depth: int,
+                    ndepths: Sequence[int], ratios: Sequence[float]):
+    """-> relproj [3,B,V-1,12], half_range [3] (device)."""
+    p1, p2, p3 = (_f32c(p, "proj") for p in proj)
+    dv = _f32c(depth_values, "depth_values")
+    B, V = p1.shape[0], p1.shape[1]
+    relproj = torch.empty((3, B, V - 1, 12), device=p1.device, dtype=torch.float32)
+    half = torch.empty((3,), device=p1.device, dtype=torch.float32)
+    nd = (ctypes.c_int * 3)(*[int(x) for x in ndepths])
+    rt = (ctypes.c_double * 3)(*[float(x) for x in ratios])
+    _check(lib().adamvs_cascade_prepare(_p(p1), _p(p2), _p(p3), _p(dv), dv.shape[1], B, V, interval_mode,
+                                        int(num_depth), nd, rt, _p(relproj), _p(half), _stream()), "cascade_prepare")
+    return relproj, half
+
+
+def pair_score(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, D: int) -> torch.Tensor:
+    feat = _f32c(feat, "feat")
+    B, V, C, h, w = feat.shape
+    out = torch.empty((B, V - 1, D, h, w), device=feat.device, dtype=torch.float32)
+    _check(lib().adamvs_pair_score_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
+                                       B, V, C, D, h, w, _stream()), "pair_score")
+    return out
+
+
+def resize_bilinear(x: torch.Tensor, ho: int, wo: int) -> torch.Tensor:
+    """x [..., hi, wi] -> [..., ho, wo], align_corners=False."""
+    x = _f32c(x, "x")
+    lead = x.shape[:-2]
+    hi, wi = x.shape[-2:]
+    n = 1
+    for s in lead:
+        n *= int(s)
+    out = torch.empty((*lead, ho, wo), device=x.device, dtype=torch.float32)
+    _check(lib().adamvs_resize_bilinear_f32(_p(x), _p(out), n, hi, wi, ho, wo, _stream()), "resize_bilinear")
+    return out
+
+
+def fused_volume(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, weights: torch.Tensor, eps_mode: int,
+                 D: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    feat = _f32c(feat, "feat")
+    B, V, C, h, w = feat.shape
+    weights = _f32c(weights, "weights")
+    assert tuple(weights.shape) == (B, V - 1, h, w), (weights.shape, (B, V - 1, h, w))
+    if out is None:
+        out = torch.empty((B, C, D, h, w), device=feat.device, dtype=torch.float32)
+    _check(lib().adamvs_fused_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(weights), eps_mode,
+                                         _p(out), B, V, C, D, h, w, _stream()), "fused_volume")
+    return out
+
+
+def regnet_workspace_floats(B, C, D, h, w, out_up) -> int:
+    return int(lib().adamvs_regnet_red_workspace_floats(B, C, D, h, w, int(out_up)))
+
+
+def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob_mode: int,
+               workspace: Optional[torch.Tensor] = None, want_logits: bool = False):
+    """volume [B,C,D,h,w] -> depth, conf [B,Ho,Wo] (+ logits [B,D,Ho,Wo] when asked).
+    `weights`: name -> contiguous fp32 CUDA tensor in the reference layouts (see RegnetWeights)."""
+    volume = _f32c(volume, "volume")
+    B, C, D, h, w = volume.shape
+    Ho, Wo = (2 * h, 2 * w) if out_up else (h, w)
+    need = regnet_workspace_floats(B, C, D, h, w, out_up)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), device=volume.device, dtype=torch.float32)
+    depth = torch.empty((B, Ho, Wo), device=volume.device, dtype=torch.float32)
+    conf = torch.empty((B, Ho, Wo), device=volume.device, dtype=torch.float32)
+    logits = torch.empty((B, D, Ho, Wo), device=volume.device, dtype=torch.float32) if want_logits else None
+    keep = {k: _f32c(v, k) for k, v in weights.items()}
+    st = RegnetWeights(**{k: v.data_ptr() for k, v in keep.items()})
+    _check(lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
+                                       _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
+                                       B, C, D, h, w, _stream()), "regnet_red")
+    return (depth, conf, logits) if want_logits else (depth, conf)
+
+
+def softmax_regress(logits: torch.Tensor, hyp: Hyp, prob_mode: int, n_per_batch: int = 1):
+    """logits [N,D,h,w] -> depth, conf [N,h,w]."""
+    logits = _f32c(logits, "logits")
+    N, D, h, w = logits.shape
+    depth = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
+    conf = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
+    _check(lib().adamvs_softmax_regress_f32(_p(logits), *hyp.args(), prob_mode, _p(depth), _p(conf),
+                                            N, n_per_batch, D, h, w, _stream()), "softmax_regress")
+    return depth, conf

@@ -1,0 +1,127 @@
+/*
+ * adamvs_b200 — C ABI of the B200-native (sm_100a) Ada-MVS cascade cost-volume hot path.
+ *
+ * The reference (gpcv-liujin/Ada-MVS, pure Python/PyTorch) has no FFI or plugin layer; its seam
+ * for this path is the Python module `models.adamvs` (train_whu.py:100, predict_whu.py:74).  The
+ * entry points below are what a binding for that seam calls: each one replaces a group of ATen
+ * op sequences in the reference, cited per function (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless named `host_*`;
+ *   - tensors are row-major with the dimension order written in the comment (x / width fastest);
+ *   - nothing allocates, nothing synchronises, nothing touches the legacy default stream: work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*) of the CURRENT device;
+ *   - re-entrant and free of global mutable state (safe under nn.DataParallel's thread-per-GPU);
+ *   - return value: 0 on success, >0 a cudaError_t from a launch, <0 an ADAMVS_E* argument error.
+ */
+#ifndef ADAMVS_B200_H
+#define ADAMVS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADAMVS_ABI_VERSION 1
+
+#define ADAMVS_EINVAL   (-1)   /* bad shape / null pointer / unsupported size               */
+#define ADAMVS_ENOSPACE (-2)   /* workspace smaller than adamvs_*_workspace_floats() says   */
+
+/* depth-hypothesis source (models/module.py:646-663 get_depth_range_samples) */
+#define ADAMVS_HYP_PLANES    0 /* hyp_src = depth_values [B,ncol]: d_k = dv[b,0] + k*(dv[b,1]-dv[b,0])/(D-1)      */
+#define ADAMVS_HYP_PER_PIXEL 1 /* hyp_src = cur_depth [B,h,w]: lo = cur - *half_range, hi = cur + *half_range,
+                                  d_k = lo + k*((hi-lo)/(D-1))                                                     */
+
+/* where the 1e-5 goes in the view-weighted mean */
+#define ADAMVS_EPS_NUMERATOR   0 /* (1e-5 + sum_v w_v ref warp_v) / sum_v w_v      DepthNet0, adamvs.py:261-262,290,301 */
+#define ADAMVS_EPS_DENOMINATOR 1 /* sum_v w_v ref warp_v / (1e-5 + sum_v w_v)      InferDepthNet0, adamvs.py:496-512    */
+
+/* probability convention of the regression */
+#define ADAMVS_PROB_SOFTMAX 0 /* softmax over D, sum p d, max p                     adamvs.py:306-310, module.py:617-625 */
+#define ADAMVS_PROB_EXP_EPS 1 /* e=exp(logit) unshifted, sum d e/(sum e+1e-10), max e/(sum e+1e-10)  adamvs.py:516-531   */
+
+/* interval convention of the cascade */
+#define ADAMVS_INTERVAL_LAST_COLUMN 0 /* interval = depth_values[0,ncol-1]                  adamvs.py:346 */
+#define ADAMVS_INTERVAL_FROM_RANGE  1 /* interval = (dv[0,ncol-1] - dv[0,0]) / num_depth    adamvs.py:569-571 */
+
+int adamvs_abi_version(void);
+
+/* Once per forward, replaces torch.inverse+matmul of models/module.py:539 (544 host-syncing calls per
+ * depth map in the reference) and the Python-double scalar arithmetic of adamvs.py:344-347,379-380 /
+ * 569-571,603-604.  For each stage s and batch item b and source view v (1..V-1):
+ *   relproj[s][b][v-1] = { rot(3x3 row-major), trans(3) } of  proj_s[b,v] * inverse(proj_s[b,0]),
+ * evaluated in fp64 and rounded once to fp32;
+ *   half_range[s] = (float)( (ndepths[s] / 2.0) * (ratios[s] * interval) ), interval in fp64 from batch item 0.
+ * proj_s*: [B,V,4,4]; depth_values: [B,ncol]; relproj: [3,B,V-1,12]; half_range: [3]. */
+int adamvs_cascade_prepare(const float* proj_s1, const float* proj_s2, const float* proj_s3,
+                           const float* depth_values, int ncol, int B, int V,
+                           int interval_mode, int num_depth,
+                           const int* host_ndepths, const double* host_ratios,
+                           float* relproj, float* half_range, void* stream);
+
+/* K1 — stage-1 pairwise matching score; replaces homo_warping_float + product + mean(dim=1)
+ * (module.py:527-568, adamvs.py:269-272 / 472-478).
+ *   score[b,v,k,y,x] = (1/C) sum_c feat[b,0,c,y,x] * bilinear(feat[b,v+1,c], u_v(x,y,d_k))
+ * feat: [B,V,C,h,w]; relproj: [B,V-1,12] (this stage's slice); score: [B,V-1,D,h,w]. */
+int adamvs_pair_score_f32(const float* feat, const float* relproj,
+                          int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                          float* score, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* Bilinear resize with align_corners=False of N planes (F.interpolate at adamvs.py:296,505):
+ * in [N,hi,wi] -> out [N,ho,wo]. */
+int adamvs_resize_bilinear_f32(const float* in, float* out, int N, int hi, int wi, int ho, int wo, void* stream);
+
+/* K2 — fused homography warp + product + per-view weighted aggregation; replaces the whole of
+ * adamvs.py:285-301 (DepthNet0) / :495-512 (InferDepthNet0) including every per-view warped volume.
+ *   volume[b,c,k,y,x] per ADAMVS_EPS_* with w_v = weights[b,v,y,x] (already at h x w).
+ * feat: [B,V,C,h,w]; weights: [B,V-1,h,w]; volume: [B,C,D,h,w]. */
+int adamvs_fused_volume_f32(const float* feat, const float* relproj,
+                            int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                            const float* weights, int eps_mode,
+                            float* volume, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* K3 (+K4 fused) — recurrent conv-GRU encoder-decoder over the D planes with the softmax regression
+ * folded into the last layer; replaces CostRegNetRED.forward / SliceCostRegNetRED.forward
+ * (adamvs.py:172-195 / 415-424), ConvGRUCell.forward (module.py:24-52) and the regression
+ * (adamvs.py:306-310 / 516-531, module.py:617-625).
+ * Weights are device pointers in the reference's own layouts:
+ *   conv1_w [8,C,3,3]; gates1_w [16,16,3,3] b[16]; cand1_w [8,16,3,3] b[8]; conv2_w [16,8,3,3];
+ *   gates2_w [32,32,3,3] b[32]; cand2_w [16,32,3,3] b[16]; up1_w [16,8,3,3] (ConvTranspose2d) b[8];
+ *   out_w [8,1,3,3] (ConvTranspose2d, out_up=1) or [1,8,3,3] (Conv2d, out_up=0), b[1]. */
+typedef struct adamvs_regnet_weights {
+    const float *conv1_w;
+    const float *gates1_w, *gates1_b;
+    const float *cand1_w, *cand1_b;
+    const float *conv2_w;
+    const float *gates2_w, *gates2_b;
+    const float *cand2_w, *cand2_b;
+    const float *up1_w, *up1_b;
+    const float *out_w, *out_b;
+} adamvs_regnet_weights;
+
+size_t adamvs_regnet_red_workspace_floats(int B, int C, int D, int h, int w, int out_up);
+
+/* volume: [B,C,D,h,w]; hypotheses as for K1/K2 (defined on the h x w grid; when out_up they are
+ * bilinearly upsampled x2, align_corners=False, per module.py:622 / adamvs.py:522);
+ * depth, conf: [B,Ho,Wo] with Ho,Wo = 2h,2w if out_up else h,w; logits_out: optional [B,D,Ho,Wo] or NULL.
+ * h and w must be even. */
+int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_weights* host_weights,
+                          int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                          int out_up, int prob_mode,
+                          float* workspace, size_t workspace_floats,
+                          float* depth, float* conf, float* logits_out,
+                          int B, int C, int D, int h, int w, void* stream);
+
+/* K4 standalone — softmax over D + expectation + max for a materialised logit volume (the stage-1
+ * pair branch: adamvs.py:274-283 / 481-489).  logits: [N,D,h,w]; hypothesis batch index = n / n_per_batch;
+ * depth, conf: [N,h,w]. Hypotheses are taken at the logits' own resolution. */
+int adamvs_softmax_regress_f32(const float* logits,
+                               int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                               int prob_mode, float* depth, float* conf,
+                               int N, int n_per_batch, int D, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAMVS_B200_H */

@@ -1,0 +1,283 @@
+"""GPU parity tests proper: every C-ABI kernel and the whole drop-in forward against the oracle
+(oracle/adamvs_oracle.py, CPU fp32) on the same seeded inputs, and against the committed reference
+outputs in tests/golden.  Tolerances are the north_star's: depth within 1e-4 relative, probability
+within 1e-4 absolute per pixel (fp32 path); intermediates within 2e-4 * max|.|."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import adamvs_oracle as O
+from tests.helpers import abs_err, load_golden, make_case, rebuild_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEPTH_RTOL = 1e-4
+PROB_ATOL = 1e-4
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from adamvs_b200 import ops
+    return ops
+
+
+def _model(cls, sd, ndepths, num_depth=192):
+    from models.adamvs import AdaMVSNet, Infer_AdaMVSNet
+    if cls == "whole":
+        m = AdaMVSNet(ndepths=list(ndepths), depth_intervals_ratio=[4.0, 2.0, 1.0])
+    else:
+        m = Infer_AdaMVSNet(num_depth=num_depth, ndepths=list(ndepths), depth_intervals_ratio=[4.0, 2.0, 1.0])
+    m.load_state_dict(sd)
+    return m.to(_dev()).eval()
+
+
+def _to_dev(proj):
+    return {k: v.to(_dev()) for k, v in proj.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels one by one
+# ------------------------------------------------------------------------------------------------
+
+def test_library_loaded_is_in_tree():
+    ops = _ops()
+    assert ops.lib().adamvs_abi_version() == 1
+    assert ops.LIB_PATH.endswith("adamvs_b200/libadamvs_b200.so")
+
+
+def test_cascade_prepare_matches_float64_inverse():
+    ops = _ops()
+    _, proj, dv2 = __import__("adamvs_b200.synth", fromlist=["x"]).make_sample(2, 64, 96, 5, seed=9)
+    relproj, half = ops.cascade_prepare([proj[k].to(_dev()) for k in ("stage1", "stage2", "stage3")],
+                                        dv2.to(_dev()), ops.INTERVAL_FROM_RANGE, 192, [48, 32, 8], [4.0, 2.0, 1.0])
+    for s, k in enumerate(("stage1", "stage2", "stage3")):
+        p = proj[k].double()
+        rel = p[:, 1:] @ torch.linalg.inv(p[:, :1])
+        want = torch.cat([rel[:, :, :3, :3].reshape(2, 4, 9), rel[:, :, :3, 3]], -1).float()
+        assert torch.equal(relproj[s].cpu(), want) or abs_err(relproj[s].cpu(), want) <= 1e-6 * float(want.abs().max())
+    interval = (float(dv2[0, 1]) - float(dv2[0, 0])) / 192
+    want_half = torch.tensor([48 / 2 * (4.0 * interval), 32 / 2 * (2.0 * interval), 8 / 2 * (1.0 * interval)],
+                             dtype=torch.float64).float()
+    assert torch.equal(half.cpu(), want_half)
+
+
+def test_resize_matches_interpolate():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 4, 24, 36, generator=g)
+    for ho, wo in ((48, 72), (96, 144), (24, 36), (31, 50)):
+        got = ops.resize_bilinear(x.to(_dev()), ho, wo).cpu()
+        want = F.interpolate(x, size=[ho, wo], mode="bilinear", align_corners=False)
+        assert abs_err(got, want) < 2e-7
+
+
+@pytest.mark.parametrize("C,D,h,w", [(32, 8, 16, 24), (16, 5, 32, 48), (8, 3, 30, 50)])
+def test_pair_score_and_fused_volume_vs_oracle(C, D, h, w):
+    """K1 and K2 (both epsilon conventions, plane and per-pixel hypotheses) against the oracle's
+    warp -> product -> weighted mean."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    B, V = 2, 5
+    g = torch.Generator().manual_seed(C + D)
+    feat = torch.randn(B, V, C, h, w, generator=g)
+    cams = synth.make_cameras(h, w, V - 1)["stage3"]                      # full-res cameras of an h x w image
+    proj = torch.stack([cams, synth.make_cameras(h, w, V - 1, jitter_seed=4)["stage3"]])
+    dv = torch.tensor([[520.0, 680.0], [540.0, 660.0]])
+    wts = torch.rand(B, V - 1, h, w, generator=g) * 0.9 + 0.05
+    relproj, half = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 192,
+                                        [D, D, D], [4.0, 2.0, 1.0])
+    cur = 600 + 20 * torch.randn(B, h, w, generator=g)
+    interval = (float(dv[0, 1]) - float(dv[0, 0])) / 192
+    for mode in ("planes", "pixel"):
+        if mode == "planes":
+            hyp = ops.Hyp(ops.HYP_PLANES, dv.to(_dev()))
+            hyps = O.depth_hypotheses(dv, D, 0.0, [B, h, w])
+        else:
+            hyp = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half[1:2])
+            hyps = O.depth_hypotheses(cur, D, 2.0 * interval, [B, h, w])
+        prods = [feat[:, 0].unsqueeze(2) * O.homography_warp(feat[:, v], proj[:, v], proj[:, 0], hyps)
+                 for v in range(1, V)]
+        score_want = torch.stack([p.mean(1) for p in prods], 1)
+        score = ops.pair_score(feat.to(_dev()), relproj[0], hyp, D).cpu()
+        assert abs_err(score, score_want) < 2e-4 * float(score_want.abs().max()), mode
+        num = sum(p * wts[:, v].unsqueeze(1).unsqueeze(1) for v, p in enumerate(prods))
+        wsum = wts.sum(1).unsqueeze(1).unsqueeze(1)
+        for eps_mode, want in ((ops.EPS_NUMERATOR, (1e-5 + num) / wsum), (ops.EPS_DENOMINATOR, num / (1e-5 + wsum))):
+            got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, wts.to(_dev()), eps_mode, D).cpu()
+            assert abs_err(got, want) < 2e-4 * float(want.abs().max()), (mode, eps_mode)
+
+
+def test_fused_volume_zero_padding_and_behind_camera():
+    """Out-of-image taps contribute zero per corner (grid_sample zeros padding); Z<=0 gives zeros."""
+    ops = _ops()
+    B, V, C, D, h, w = 1, 2, 8, 2, 8, 12
+    feat = torch.ones(B, V, C, h, w)
+    proj = torch.eye(4).repeat(B, V, 1, 1)
+    proj[0, 1, 0, 3] = 5.5 * 600.0          # shifts u by +5.5 px at depth 600 -> right part leaves the image
+    dv = torch.tensor([[600.0, 600.0001]])
+    relproj, _ = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 1, [D] * 3, [1.0] * 3)
+    hyp = ops.Hyp(ops.HYP_PLANES, dv.to(_dev()))
+    hyps = O.depth_hypotheses(dv, D, 0.0, [B, h, w])
+    want = O.homography_warp(feat[:, 1], proj[:, 1], proj[:, 0], hyps)
+    got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, torch.ones(B, 1, h, w, device=_dev()),
+                           ops.EPS_DENOMINATOR, D).cpu() * (1 + 1e-5)
+    assert abs_err(got, want) < 1e-5
+    assert abs(float(want[0, 0, 0, 0, w - 6]) - 0.5) < 1e-4 and float(want[0, 0, 0, 0, w - 5]) == 0.0
+    proj[0, 1, 2, 2] = -1.0                  # source camera looks the other way: Z < 0 everywhere
+    relproj, _ = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 1, [D] * 3, [1.0] * 3)
+    got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, torch.ones(B, 1, h, w, device=_dev()), ops.EPS_DENOMINATOR, D)
+    assert float(got.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,D,h,w,up,prob", [(32, 6, 16, 24, True, "softmax"), (16, 4, 32, 48, True, "exp"),
+                                             (8, 3, 64, 96, False, "softmax"), (8, 2, 34, 46, False, "exp")])
+def test_regnet_red_vs_oracle(C, D, h, w, up, prob):
+    """K3 with the regression folded in: logits, depth and confidence against the oracle's plane loop."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    B = 2
+    g = torch.Generator().manual_seed(h + D)
+    i = {32: 0, 16: 1, 8: 2}[C]
+    assert up == (i < 2)
+    sd = synth.fill_state_dict(synth.state_dict_shapes(8), 21)
+    p = f"DepthNet.{i}.reg_fuse"
+    sd[p + ".upconv2d.weight"] = sd[p + ".upconv2d.weight"] * 20      # sharpen the logits
+    vol = torch.randn(B, C, D, h, w, generator=g)
+    cur = 600 + 10 * torch.randn(B, h, w, generator=g)
+    half_range = torch.tensor([3.3], dtype=torch.float32)
+    hyps = O.depth_hypotheses(cur, D, float(half_range) / (D / 2), [B, h, w])
+    logits_want = O.red_regulariser(sd, p, vol, up)
+    Ho, Wo = logits_want.shape[2:]
+    hy = O._resize(hyps, (Ho, Wo)) if up else hyps
+    if prob == "softmax":
+        pr = F.softmax(logits_want, 1)
+        depth_want, conf_want = (pr * hy).sum(1), pr.max(1)[0]
+        mode = ops.PROB_SOFTMAX
+    else:
+        e = logits_want.exp()
+        den = e.sum(1) + 1e-10
+        depth_want, conf_want = (e * hy).sum(1) / den, e.max(1)[0] / den
+        mode = ops.PROB_EXP_EPS
+    names = {"conv1_w": ".conv1.conv.weight", "gates1_w": ".conv_gru1.conv_gates.0.weight",
+             "gates1_b": ".conv_gru1.conv_gates.0.bias", "cand1_w": ".conv_gru1.convc.0.weight",
+             "cand1_b": ".conv_gru1.convc.0.bias", "conv2_w": ".conv2.conv.weight",
+             "gates2_w": ".conv_gru2.conv_gates.0.weight", "gates2_b": ".conv_gru2.conv_gates.0.bias",
+             "cand2_w": ".conv_gru2.convc.0.weight", "cand2_b": ".conv_gru2.convc.0.bias",
+             "up1_w": ".upconv1.weight", "up1_b": ".upconv1.bias", "out_w": ".upconv2d.weight", "out_b": ".upconv2d.bias"}
+    wd = {k: sd[p + v].to(_dev()) for k, v in names.items()}
+    hyp = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half_range.to(_dev()))
+    depth, conf, logits = ops.regnet_red(vol.to(_dev()), wd, hyp, up, mode, want_logits=True)
+    assert abs_err(logits.cpu(), logits_want) < 1e-4 * max(1.0, float(logits_want.abs().max()))
+    assert rel_err(depth.cpu(), depth_want) < DEPTH_RTOL
+    assert abs_err(conf.cpu(), conf_want) < PROB_ATOL
+
+
+def test_softmax_regress_vs_torch():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    N, D, h, w = 8, 48, 12, 20
+    logits = 6 * torch.randn(N, D, h, w, generator=g)
+    dv = torch.tensor([[520.0, 680.0], [500.0, 700.0]])
+    hyps = O.depth_hypotheses(dv, D, 0.0, [2, h, w]).repeat_interleave(4, 0)
+    pr = F.softmax(logits, 1)
+    depth, conf = ops.softmax_regress(logits.to(_dev()), ops.Hyp(ops.HYP_PLANES, dv.to(_dev())), ops.PROB_SOFTMAX, 4)
+    assert rel_err(depth.cpu(), (pr * hyps).sum(1)) < 2e-6
+    assert abs_err(conf.cpu(), pr.max(1)[0]) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# whole forward
+# ------------------------------------------------------------------------------------------------
+
+def _compare_outputs(out, want_depth, want_conf, tag):
+    d_err = rel_err(out["depth"].cpu(), want_depth)
+    p_err = abs_err(out["photometric_confidence"].cpu(), want_conf)
+    assert d_err < DEPTH_RTOL, f"{tag}: depth rel err {d_err:.3e}"
+    assert p_err < PROB_ATOL, f"{tag}: prob abs err {p_err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["small_d8", "batch2_d8", "full_d48"])
+@pytest.mark.parametrize("cls", ["whole", "stream"])
+def test_forward_matches_reference_golden(name, cls):
+    """The CUDA path against the reference's own outputs (fixtures generated from /root/reference)."""
+    g = load_golden(name)
+    sd, imgs, proj, dv2, dv3, meta = rebuild_case(g)
+    m = _model(cls, sd, meta["ndepths"], meta["num_depth"])
+    dv = dv3 if cls == "whole" else dv2
+    out = m(imgs.to(_dev()), _to_dev(proj), dv.to(_dev()))
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], g[f"{cls}_{s}_depth"], g[f"{cls}_{s}_conf"], f"{name}/{cls}/{s}")
+        assert abs_err(torch.stack(out[s]["pair_confidence"][:4], 1).cpu(), g[f"{cls}_{s}_pair_conf4"]) < PROB_ATOL
+        assert len(out[s]["pair_confidence"]) == int(g[f"{cls}_{s}_pair_conf_len"])
+        if s == "stage1":
+            assert rel_err(torch.stack(out[s]["pair_result"], 1).cpu(), g[f"{cls}_{s}_pair_result"]) < DEPTH_RTOL
+        else:
+            assert out[s]["pair_result"] == []
+    assert out["depth"] is out["stage3"]["depth"]
+    for leaf in (out["depth"], out["photometric_confidence"], *out["pair_confidence"][:4]):
+        assert isinstance(leaf, torch.Tensor)
+
+
+def test_intermediates_match_reference_golden():
+    from adamvs_b200 import cascade
+    g = load_golden("small_d8")
+    sd, imgs, proj, dv2, dv3, meta = rebuild_case(g)
+    m = _model("whole", sd, meta["ndepths"])
+    cap = {}
+    cascade.forward(m, imgs.to(_dev()), _to_dev(proj), dv3.to(_dev()), capture=cap)
+    for i, s in enumerate(("stage1", "stage2", "stage3")):
+        want = g[f"features_{s}"]
+        assert abs_err(cap[s]["features"].cpu(), want) < 2e-5 * float(np.abs(want).max())
+        want = g[f"whole_s{i + 1}_fused"]
+        assert abs_err(cap[s]["fused"].cpu(), want) < 2e-4 * float(np.abs(want).max()), s
+        want = g[f"whole_s{i + 1}_logits"]
+        assert abs_err(cap[s]["logits"].cpu(), want) < 2e-4 * max(1.0, float(np.abs(want).max())), s
+    want = g["whole_s1_pair_score"]
+    assert abs_err(cap["stage1"]["pair_score"].cpu(), want) < 2e-4 * float(np.abs(want).max())
+
+
+@pytest.mark.parametrize("cls", ["whole", "stream"])
+def test_forward_full_size_vs_oracle(cls):
+    """BASELINE config 2: 1 ref + 4 src views, 768x384, ndepths 48/32/8, calibrated seeded weights."""
+    sd, imgs, proj, dv2, dv3 = make_case(1, 384, 768, (48, 32, 8), 192, 60.0, 31, 17, O.feature_net)
+    if cls == "whole":
+        want = O.adamvs_forward(sd, imgs, proj, dv3)
+    else:
+        want = O.infer_adamvs_forward(sd, imgs, proj, dv2, num_depth=192)
+    m = _model(cls, sd, (48, 32, 8), 192)
+    out = m(imgs.to(_dev()), _to_dev(proj), (dv3 if cls == "whole" else dv2).to(_dev()))
+    assert tuple(out["stage1"]["depth"].shape) == (1, 192, 384)
+    assert tuple(out["depth"].shape) == (1, 384, 768)
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], want[s]["depth"], want[s]["photometric_confidence"], f"full/{cls}/{s}")
+    conf = want["stage1"]["photometric_confidence"]                  # not the vacuous 1/D regime:
+    assert float(conf.max()) > 5.0 / 48 and float(conf.std()) > 2e-3
+    assert float(want["stage3"]["photometric_confidence"].max()) > 0.5
+
+
+def test_dataparallel_wrapper_and_module_prefix():
+    """predict_whu.py wraps the model in nn.DataParallel and loads 'module.'-prefixed keys."""
+    g = load_golden("small_d8")
+    sd, imgs, proj, dv2, dv3, meta = rebuild_case(g)
+    from models.adamvs import Infer_AdaMVSNet
+    m = torch.nn.DataParallel(Infer_AdaMVSNet(num_depth=meta["num_depth"], ndepths=list(meta["ndepths"]),
+                                              depth_intervals_ratio=[4.0, 2.0, 1.0]), device_ids=[0])
+    m.cuda()
+    m.load_state_dict({"module." + k: v for k, v in sd.items()})
+    m.eval()
+    with torch.no_grad():
+        out = m(imgs.cuda(), {k: v.cuda() for k, v in proj.items()}, dv2.cuda())
+    _compare_outputs(out, g["stream_stage3_depth"], g["stream_stage3_conf"], "dp")
+
+
+def test_cpu_tensors_are_refused():
+    from adamvs_b200 import ops
+    g = load_golden("small_d8")
+    sd, imgs, proj, dv2, dv3, meta = rebuild_case(g)
+    m = _model("whole", sd, meta["ndepths"])
+    with pytest.raises(ops.AdamvsError):
+        m(imgs, proj, dv3)
