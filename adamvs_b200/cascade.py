@@ -61,7 +61,9 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
 
     imgs = imgs.float()
     depth_values = depth_values.float().contiguous()
-    feats = extract_features(net, imgs)
+    ops.set_tag("all")
+    with ops.timed("featurenet_cudnn", 0):
+        feats = extract_features(net, imgs)
     relproj, half = ops.cascade_prepare(
         [proj_matrices[k] for k in _STAGES], depth_values,
         ops.INTERVAL_FROM_RANGE if stream_conv else ops.INTERVAL_LAST_COLUMN,
@@ -74,6 +76,7 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
     stage1_w = None          # [B,Vs,h1,w1]
     prev_w = None            # weights as resized by the previous stage (predict class chains them)
     for i, key in enumerate(_STAGES):
+        ops.set_tag(key)
         feat = feats[key]
         _, _, C, h, w = feat.shape
         D = ndepths[i]
@@ -85,7 +88,7 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
         pair_depths: List[torch.Tensor] = []
         if stage1_w is None:
             score = ops.pair_score(feat, relproj[i], hyp, D)                     # [B,Vs,D,h,w]
-            with _true_fp32():
+            with ops.timed("pair_unet_cudnn", 0), _true_fp32():
                 pair_logits = net.DepthNet[i].reg(score.reshape(B * (V - 1), D, h, w))
             pd, pc = ops.softmax_regress(pair_logits, hyp, ops.PROB_SOFTMAX, n_per_batch=V - 1)
             stage1_w = pc.reshape(B, V - 1, h, w)

@@ -21,6 +21,7 @@
 //   7 up1     y   = relu(convT3x3 s2 (h2) + b + h1)                      16 -> 8
 //   8 out     logit = convT3x3 s2 (y) + b  (stages 1-2) | conv3x3(y)+b (stage 3); online softmax update
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace adamvs {
 
@@ -41,6 +42,8 @@ struct ConvArgs {
     const float* hstate;   // GATES / CAND: h [B,HC,h,w]
     const float* ugate;    // CAND: u [B,HC,h,w]
     int hin, win, hout, wout;
+    int planesA, planesB;  // channels per batch item of the tensors behind inA / inB (TMA plane coordinate)
+    int k;                 // depth-plane coordinate of inA (conv1 reads plane k of the cost volume)
 };
 
 template <int STRIDE, int TW, int TH>
@@ -191,6 +194,227 @@ conv3x3_kernel(ConvArgs a) {
                     const float u = a.ugate[o];
                     a.out0[o] = u * a.hstate[o] + (1.f - u) * cand;
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed variant (the fast path; needs w % 4 == 0).  The whole input tile of the block — all CIN
+// channels with the 1-pixel halo, zero-filled outside the image by the TMA unit — is requested up
+// front as CIN/8 boxes, each signalling its own mbarrier, so the FFMA loop on chunk c overlaps the
+// arrival of chunks c+1.. and no thread spends instructions on address arithmetic or bounds checks.
+// Small planes (stage 1, or B = 1) get more parallelism from PY = 1 patches and from splitting the
+// input-channel chunks over KSPLIT warps groups, reduced through shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int CA, int CB, int COUT, int COB, int STRIDE, int TH, int PY, int KSPLIT>
+struct TmaCfg {
+    static constexpr int TW = 32;
+    static constexpr int CIN = CA + CB, NCHUNK = CIN / CK, NCOG = COB / COT;
+    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
+    // the innermost TMA start coordinate must be 16-byte aligned (tools/tma_probe.cu), so the box
+    // starts 4 columns left of the tile; the 1-pixel halo column is tile column 3
+    static constexpr int IP = STRIDE == 1 ? TW + 8 : 2 * TW + 8;
+    static constexpr int GROUP = (TW / PX) * (TH / PY);
+    static constexpr int NT = GROUP * NCOG * KSPLIT;
+    static constexpr int CHUNK_FLOATS = CK * IH * IP;
+    static constexpr int NACC = PY * PX * COT;
+    static constexpr int RED_FLOATS = (KSPLIT - 1) * GROUP * NCOG * NACC;
+    static constexpr int W_FLOATS = CIN * 9 * COB;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(NCHUNK * CHUNK_FLOATS + W_FLOATS + RED_FLOATS) + 8 * NCHUNK;
+    static_assert(NCHUNK % KSPLIT == 0, "KSPLIT must divide the chunk count");
+    static_assert((GROUP * NCOG) % 32 == 0, "warps must be uniform in (k-slice, channel group)");
+    static_assert(TH % PY == 0 && CA % CK == 0 && CB % CK == 0 && COB % COT == 0 && COUT % COB == 0, "bad blocking");
+};
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT>
+__global__ void __launch_bounds__(TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>::NT)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
+    using G = TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>;
+    constexpr int TW = G::TW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sIn = reinterpret_cast<float*>(smem_raw);                 // [NCHUNK][CK][IH][IP]
+    float* sW = sIn + G::NCHUNK * G::CHUNK_FLOATS;                   // [CIN][9][COB]
+    float* sRed = sW + G::W_FLOATS;                                  // [KSPLIT-1][NACC][GROUP*NCOG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + G::RED_FLOATS);
+
+    const int tid = threadIdx.x;
+    const int ks = tid / (G::GROUP * G::NCOG);
+    const int gt = tid - ks * (G::GROUP * G::NCOG);                  // thread index inside the k-slice
+    const int cog = gt / G::GROUP;
+    const int t = gt - cog * G::GROUP;
+    const int tx = t % (TW / PX), ty = t / (TW / PX);
+    const int tiles_x = (a.wout + TW - 1) / TW;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int cob = blockIdx.y;
+    const int b = blockIdx.z;
+    const int ox0 = tile_x * TW, oy0 = tile_y * TH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < G::NCHUNK; ++c) mbar_init(&bars[c], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < G::NCHUNK; ++c) {
+            mbar_expect_tx(&bars[c], G::CHUNK_FLOATS * 4);
+            const bool fromA = c * CK < CA;
+            const int plane = fromA ? b * a.planesA + c * CK : b * a.planesB + (c * CK - CA);
+            tma_load_4d(sIn + c * G::CHUNK_FLOATS, fromA ? &tmA : &tmB, &bars[c],
+                        ox0 * STRIDE - 4, oy0 * STRIDE - 1, fromA ? a.k : 0, plane);
+        }
+    }
+    for (int i = tid; i < G::W_FLOATS; i += G::NT) {
+        const int col = i % COB, ct = i / COB;
+        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
+    }
+    __syncthreads();
+
+    float acc[PY][PX][COT];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int c = 0; c < COT; ++c) acc[j][p][c] = 0.f;
+
+#pragma unroll 1
+    for (int chunk = ks; chunk < G::NCHUNK; chunk += KSPLIT) {
+        mbar_wait(&bars[chunk], 0);
+        const float* sC = sIn + chunk * G::CHUNK_FLOATS;
+#pragma unroll 2
+        for (int c = 0; c < CK; ++c) {
+            const float* wrow = sW + ((chunk * CK + c) * 9) * COB + cog * COT;
+            const float* irow = sC + (c * G::IH) * G::IP;
+            if (STRIDE == 1) {
+#pragma unroll
+                for (int r = 0; r < PY + 2; ++r) {
+                    const float* ip = irow + (PY * ty + r) * G::IP + PX * tx;
+                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
+                    const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
+                    const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
+                    const float in[6] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x};      // tile columns 4tx+3 .. 4tx+8
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int j = r - ky;
+                        if (j < 0 || j >= PY) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[p + kx], wv[co], acc[j][p][co]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2 * PY + 1; ++r) {
+                    const float* ip = irow + (2 * PY * ty + r) * G::IP + 2 * PX * tx;
+                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
+                    const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
+                    const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
+                    const float in[9] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};   // columns 8tx+3 .. 8tx+11
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int jj = r - ky;
+                        if (jj < 0 || (jj & 1) || jj / 2 >= PY) continue;
+                        const int j = jj / 2;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[2 * p + kx], wv[co], acc[j][p][co]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (KSPLIT > 1) {                                   // reduce the k-slices into slice 0
+        constexpr int GN = G::GROUP * G::NCOG;
+        if (ks > 0) {
+            float* dst = sRed + (size_t)(ks - 1) * G::NACC * GN + gt;
+#pragma unroll
+            for (int j = 0; j < PY; ++j)
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                    for (int c = 0; c < COT; ++c) dst[((j * PX + p) * COT + c) * GN] = acc[j][p][c];
+        }
+        __syncthreads();
+        if (ks > 0) return;
+#pragma unroll
+        for (int s = 0; s < KSPLIT - 1; ++s) {
+            const float* src = sRed + (size_t)s * G::NACC * GN + gt;
+#pragma unroll
+            for (int j = 0; j < PY; ++j)
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                    for (int c = 0; c < COT; ++c) acc[j][p][c] += src[((j * PX + p) * COT + c) * GN];
+        }
+    }
+
+    // ------------------------------------------------------------------ epilogue (float4 along x)
+    const int co_base = cob * COB + cog * COT;
+    const size_t plane = (size_t)a.hout * a.wout;
+    const int ox = ox0 + PX * tx;
+    if (ox >= a.wout) return;                           // wout % 4 == 0: a float4 is all in or all out
+    if (EPI == EPI_GATES) {
+        // r*h needs h at the output pixel: it is input channel CA + (co % HC), already in the tile
+        constexpr int HC = COUT / 2;
+        if (co_base < HC) {
+#pragma unroll
+            for (int c = 0; c < G::NCHUNK; ++c) if (c * CK >= CA) mbar_wait(&bars[c], 0);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+        const int oy = oy0 + PY * ty + j;
+        if (oy >= a.hout) continue;
+        const size_t pix = (size_t)oy * a.wout + ox;
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+            const int co = co_base + c;
+            float v[4] = {acc[j][0][c], acc[j][1][c], acc[j][2][c], acc[j][3][c]};
+            if (EPI == EPI_RELU) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) v[p] = fmaxf(v[p], 0.f);
+                *reinterpret_cast<float4*>(a.out0 + ((size_t)b * COUT + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (EPI == EPI_GATES) {
+                constexpr int HC = COUT / 2;
+                const float bc = __ldg(a.bias + co);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) v[p] = sigmoid_f(v[p] + bc);
+                if (co < HC) {
+                    const int ci = CA + co;
+                    const float4 hh = *reinterpret_cast<const float4*>(
+                        sIn + (ci / CK) * G::CHUNK_FLOATS + ((ci % CK) * G::IH + PY * ty + j + 1) * G::IP + PX * tx + 4);
+                    v[0] *= hh.x; v[1] *= hh.y; v[2] *= hh.z; v[3] *= hh.w;
+                    *reinterpret_cast<float4*>(a.out0 + ((size_t)b * HC + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    *reinterpret_cast<float4*>(a.out1 + ((size_t)b * HC + (co - HC)) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            } else {
+                const size_t o = ((size_t)b * COUT + co) * plane + pix;
+                const float bc = __ldg(a.bias + co);
+                const float4 u = *reinterpret_cast<const float4*>(a.ugate + o);
+                const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
+                const float uu[4] = {u.x, u.y, u.z, u.w}, hv[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanhf(v[p] + bc);
+                *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
     }
@@ -411,23 +635,74 @@ static cudaError_t launch_conv(const ConvArgs& a, int B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Tile choice: the largest tile that still gives every SM at least ~2 blocks.
-static int pick_tile(int hout, int wout, int B, int co_blocks) {
-    const long long want = 2LL * 148;
-    auto blocks = [&](int tw, int th) { return (long long)((wout + tw - 1) / tw) * ((hout + th - 1) / th) * B * co_blocks; };
-    if (blocks(32, 32) >= want) return 0;
-    if (blocks(32, 16) >= want) return 1;
-    return 2;
+// Fallback launcher (any even h, w): fixed 16x16 tiles.
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
+static cudaError_t launch_conv_auto(const ConvArgs& a, int B, cudaStream_t st) {
+    return launch_conv<CA, CB, COUT, COB, STRIDE, EPI, 16, 16>(a, B, st);
+}
+
+// ---- TMA path: per-layer plan (configuration + tensor maps), built once per regulariser call -----
+struct ConvPlan {
+    int cfg;                 // 0 BIG (TH16,PY2), 1 MID (TH8,PY1), 2 SMALL (TH8,PY1, split-K over all chunks)
+    CUtensorMap tA, tB;
+    ConvArgs args;
+};
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT>
+static cudaError_t launch_tma(const ConvPlan& p, int B, cudaStream_t st) {
+    using G = TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>;
+    auto kern = conv3x3_tma_kernel<CA, CB, COUT, COB, STRIDE, EPI, TH, PY, KSPLIT>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    const int tiles = ((p.args.wout + 31) / 32) * ((p.args.hout + TH - 1) / TH);
+    dim3 grid(tiles, COUT / COB, B);
+    kern<<<grid, G::NT, G::SMEM, st>>>(p.tA, p.tB, p.args);
+    return cudaGetLastError();
 }
 
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
-static cudaError_t launch_conv_auto(const ConvArgs& a, int B, cudaStream_t st) {
-    switch (pick_tile(a.hout, a.wout, B, COUT / COB)) {
-        case 0: return launch_conv<CA, CB, COUT, COB, STRIDE, EPI, 32, 32>(a, B, st);
-        case 1: return launch_conv<CA, CB, COUT, COB, STRIDE, EPI, 32, 16>(a, B, st);
-        default: return launch_conv<CA, CB, COUT, COB, STRIDE, EPI, 16, 16>(a, B, st);
+struct ConvLayer {
+    static constexpr int NCHUNK = (CA + CB) / CK;
+    static int choose_cfg(int hout, int wout, int B) {
+        const long long want = 148LL * 768;                       // ~24 warps per SM
+        const long long px = (long long)hout * wout * B;
+        const long long t_big = px / 8 * (COUT / COT), t_mid = px / 4 * (COUT / COT);
+        if (t_big >= want) return 0;
+        if (t_mid >= want || NCHUNK == 1) return 1;
+        return 2;
     }
-}
+    static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
+        p.args = a;
+        p.cfg = choose_cfg(a.hout, a.wout, B);
+        const int TH = p.cfg == 0 ? 16 : 8;
+        const int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
+        const int IP = STRIDE == 1 ? 40 : 72;
+        if (!make_tmap_4d(&p.tA, a.inA, a.win, a.hin, depthA, (long long)B * a.planesA, IP, IH, CK)) return false;
+        if (CB > 0) { if (!make_tmap_4d(&p.tB, a.inB, a.win, a.hin, 1, (long long)B * a.planesB, IP, IH, CK)) return false; }
+        else p.tB = p.tA;
+        return true;
+    }
+    static cudaError_t launch(const ConvPlan& p, int B, cudaStream_t st) {
+        switch (p.cfg) {
+            case 0: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 16, 2, 1>(p, B, st);
+            case 1: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, 1>(p, B, st);
+            default: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, NCHUNK>(p, B, st);
+        }
+    }
+};
+
+using Gates1 = ConvLayer<8, 8, 16, 16, 1, EPI_GATES>;
+using Cand1 = ConvLayer<8, 8, 8, 8, 1, EPI_CAND>;
+using Conv2 = ConvLayer<8, 0, 16, 16, 2, EPI_RELU>;
+using Gates2 = ConvLayer<16, 16, 32, 16, 1, EPI_GATES>;
+using Cand2 = ConvLayer<16, 16, 16, 16, 1, EPI_CAND>;
+template <int C> using Conv1 = ConvLayer<C, 0, 8, 8, 1, EPI_RELU>;
 
 struct Workspace {
     float *pk_conv1, *pk_gates1, *pk_cand1, *pk_conv2, *pk_gates2, *pk_cand2, *pk_up1;
@@ -508,37 +783,55 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
     const OutWeights ow{hwts->out_w, hwts->out_b};
     const RegressState rs{ws.s0, ws.s1, ws.s2};
 
+    // ---- per-layer arguments (fixed for the whole sweep; only conv1's plane index changes)
+    ConvArgs a1{}, a2{}, a3{}, a4{}, a5{}, a6{};
+    a1.inA = volume; a1.strideA_c = (long long)D * hw; a1.strideA_b = (long long)C * D * hw; a1.planesA = C;
+    a1.wpk = ws.pk_conv1; a1.out0 = ws.x1; a1.hin = h; a1.win = w; a1.hout = h; a1.wout = w;
+    a2.inA = ws.x1; a2.strideA_c = hw; a2.strideA_b = 8 * hw; a2.planesA = 8;
+    a2.inB = ws.h1; a2.strideB_c = hw; a2.strideB_b = 8 * hw; a2.planesB = 8;
+    a2.wpk = ws.pk_gates1; a2.bias = hwts->gates1_b; a2.out0 = ws.rh1; a2.out1 = ws.u1; a2.hstate = ws.h1;
+    a2.hin = h; a2.win = w; a2.hout = h; a2.wout = w;
+    a3 = a2; a3.inB = ws.rh1; a3.wpk = ws.pk_cand1; a3.bias = hwts->cand1_b; a3.out0 = ws.h1; a3.out1 = nullptr; a3.ugate = ws.u1;
+    a4.inA = ws.h1; a4.strideA_c = hw; a4.strideA_b = 8 * hw; a4.planesA = 8; a4.wpk = ws.pk_conv2; a4.out0 = ws.x2;
+    a4.hin = h; a4.win = w; a4.hout = h2; a4.wout = w2;
+    a5.inA = ws.x2; a5.strideA_c = hw2; a5.strideA_b = 16 * hw2; a5.planesA = 16;
+    a5.inB = ws.h2; a5.strideB_c = hw2; a5.strideB_b = 16 * hw2; a5.planesB = 16;
+    a5.wpk = ws.pk_gates2; a5.bias = hwts->gates2_b; a5.out0 = ws.rh2; a5.out1 = ws.u2; a5.hstate = ws.h2;
+    a5.hin = h2; a5.win = w2; a5.hout = h2; a5.wout = w2;
+    a6 = a5; a6.inB = ws.rh2; a6.wpk = ws.pk_cand2; a6.bias = hwts->cand2_b; a6.out0 = ws.h2; a6.out1 = nullptr; a6.ugate = ws.u2;
+
+    // TMA needs 16-byte global row strides at both resolutions
+    bool tma = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(volume) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0);
+    ConvPlan p1, p2, p3, p4, p5, p6;
+    if (tma) {
+        bool ok = (C == 8 ? Conv1<8>::plan(p1, a1, B, D) : C == 16 ? Conv1<16>::plan(p1, a1, B, D) : Conv1<32>::plan(p1, a1, B, D));
+        ok = ok && Gates1::plan(p2, a2, B, 1) && Cand1::plan(p3, a3, B, 1) && Conv2::plan(p4, a4, B, 1)
+                && Gates2::plan(p5, a5, B, 1) && Cand2::plan(p6, a6, B, 1);
+        tma = ok;
+    }
+
     for (int k = 0; k < D; ++k) {
-        ConvArgs a{};
-        // 1 conv1: plane k of the volume, channel stride D*h*w
-        a.inA = volume + (size_t)k * hw; a.strideA_c = (long long)D * hw; a.strideA_b = (long long)C * D * hw;
-        a.wpk = ws.pk_conv1; a.out0 = ws.x1; a.hin = h; a.win = w; a.hout = h; a.wout = w;
-        if (C == 8) ADAMVS_TRY(run_conv1<8>(a, B, st));
-        else if (C == 16) ADAMVS_TRY(run_conv1<16>(a, B, st));
-        else ADAMVS_TRY(run_conv1<32>(a, B, st));
-        // 2 gates1
-        a = ConvArgs{};
-        a.inA = ws.x1; a.strideA_c = hw; a.strideA_b = 8 * hw; a.inB = ws.h1; a.strideB_c = hw; a.strideB_b = 8 * hw;
-        a.wpk = ws.pk_gates1; a.bias = hwts->gates1_b; a.out0 = ws.rh1; a.out1 = ws.u1; a.hstate = ws.h1;
-        a.hin = h; a.win = w; a.hout = h; a.wout = w;
-        ADAMVS_TRY((launch_conv_auto<8, 8, 16, 16, 1, EPI_GATES>(a, B, st)));
-        // 3 cand1 (+ state update in place)
-        a.inB = ws.rh1; a.wpk = ws.pk_cand1; a.bias = hwts->cand1_b; a.out0 = ws.h1; a.out1 = nullptr; a.ugate = ws.u1;
-        ADAMVS_TRY((launch_conv_auto<8, 8, 8, 8, 1, EPI_CAND>(a, B, st)));
-        // 4 conv2 (stride 2)
-        a = ConvArgs{};
-        a.inA = ws.h1; a.strideA_c = hw; a.strideA_b = 8 * hw; a.wpk = ws.pk_conv2; a.out0 = ws.x2;
-        a.hin = h; a.win = w; a.hout = h2; a.wout = w2;
-        ADAMVS_TRY((launch_conv_auto<8, 0, 16, 16, 2, EPI_RELU>(a, B, st)));
-        // 5 gates2
-        a = ConvArgs{};
-        a.inA = ws.x2; a.strideA_c = hw2; a.strideA_b = 16 * hw2; a.inB = ws.h2; a.strideB_c = hw2; a.strideB_b = 16 * hw2;
-        a.wpk = ws.pk_gates2; a.bias = hwts->gates2_b; a.out0 = ws.rh2; a.out1 = ws.u2; a.hstate = ws.h2;
-        a.hin = h2; a.win = w2; a.hout = h2; a.wout = w2;
-        ADAMVS_TRY((launch_conv_auto<16, 16, 32, 16, 1, EPI_GATES>(a, B, st)));
-        // 6 cand2
-        a.inB = ws.rh2; a.wpk = ws.pk_cand2; a.bias = hwts->cand2_b; a.out0 = ws.h2; a.out1 = nullptr; a.ugate = ws.u2;
-        ADAMVS_TRY((launch_conv_auto<16, 16, 16, 16, 1, EPI_CAND>(a, B, st)));
+        if (tma) {
+            p1.args.k = k;
+            if (C == 8) ADAMVS_TRY(Conv1<8>::launch(p1, B, st));
+            else if (C == 16) ADAMVS_TRY(Conv1<16>::launch(p1, B, st));
+            else ADAMVS_TRY(Conv1<32>::launch(p1, B, st));
+            ADAMVS_TRY(Gates1::launch(p2, B, st));
+            ADAMVS_TRY(Cand1::launch(p3, B, st));
+            ADAMVS_TRY(Conv2::launch(p4, B, st));
+            ADAMVS_TRY(Gates2::launch(p5, B, st));
+            ADAMVS_TRY(Cand2::launch(p6, B, st));
+        } else {
+            a1.inA = volume + (size_t)k * hw;
+            if (C == 8) ADAMVS_TRY(run_conv1<8>(a1, B, st));
+            else if (C == 16) ADAMVS_TRY(run_conv1<16>(a1, B, st));
+            else ADAMVS_TRY(run_conv1<32>(a1, B, st));
+            ADAMVS_TRY((launch_conv_auto<8, 8, 16, 16, 1, EPI_GATES>(a2, B, st)));
+            ADAMVS_TRY((launch_conv_auto<8, 8, 8, 8, 1, EPI_CAND>(a3, B, st)));
+            ADAMVS_TRY((launch_conv_auto<8, 0, 16, 16, 2, EPI_RELU>(a4, B, st)));
+            ADAMVS_TRY((launch_conv_auto<16, 16, 32, 16, 1, EPI_GATES>(a5, B, st)));
+            ADAMVS_TRY((launch_conv_auto<16, 16, 16, 16, 1, EPI_CAND>(a6, B, st)));
+        }
         // 7 up1 + skip + relu
         {
             dim3 grid((w2 + 127) / 128, h2, B);

@@ -70,6 +70,43 @@ class AdamvsError(RuntimeError):
     pass
 
 
+# ---- instrumentation used by bench.py (off by default; never changes what is launched) -------------
+LAUNCHES = [0]          # kernels of this library enqueued so far (counted from the known launch lists)
+_timing = None          # None | dict: "<op>/<tag>" -> [(start_event, end_event), ...]
+_tag = ""
+
+
+def set_timing(sink):
+    global _timing
+    _timing = sink
+
+
+def set_tag(tag: str):
+    global _tag
+    _tag = tag
+
+
+class _timed:
+    def __init__(self, name, launches):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        LAUNCHES[0] += self.launches
+        if _timing is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _timing is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _timing.setdefault(f"{self.name}/{_tag}", []).append((self.e0, e1))
+        return False
+
+
+timed = _timed      # cascade.py brackets the torch/cuDNN parts with it (0 launches of ours)
+
+
 def _check(rc: int, what: str):
     if rc == 0:
         return
@@ -117,8 +154,9 @@ def cascade_prepare(proj: Sequence[torch.Tensor], depth_values: torch.Tensor, in
     half = torch.empty((3,), device=p1.device, dtype=torch.float32)
     nd = (ctypes.c_int * 3)(*[int(x) for x in ndepths])
     rt = (ctypes.c_double * 3)(*[float(x) for x in ratios])
-    _check(lib().adamvs_cascade_prepare(_p(p1), _p(p2), _p(p3), _p(dv), dv.shape[1], B, V, interval_mode,
-                                        int(num_depth), nd, rt, _p(relproj), _p(half), _stream()), "cascade_prepare")
+    with _timed("cascade_prepare", 2):
+        _check(lib().adamvs_cascade_prepare(_p(p1), _p(p2), _p(p3), _p(dv), dv.shape[1], B, V, interval_mode,
+                                            int(num_depth), nd, rt, _p(relproj), _p(half), _stream()), "cascade_prepare")
     return relproj, half
 
 
@@ -126,8 +164,9 @@ def pair_score(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, D: int) -> t
     feat = _f32c(feat, "feat")
     B, V, C, h, w = feat.shape
     out = torch.empty((B, V - 1, D, h, w), device=feat.device, dtype=torch.float32)
-    _check(lib().adamvs_pair_score_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
-                                       B, V, C, D, h, w, _stream()), "pair_score")
+    with _timed("pair_score", 1):
+        _check(lib().adamvs_pair_score_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
+                                           B, V, C, D, h, w, _stream()), "pair_score")
     return out
 
 
@@ -140,7 +179,8 @@ def resize_bilinear(x: torch.Tensor, ho: int, wo: int) -> torch.Tensor:
     for s in lead:
         n *= int(s)
     out = torch.empty((*lead, ho, wo), device=x.device, dtype=torch.float32)
-    _check(lib().adamvs_resize_bilinear_f32(_p(x), _p(out), n, hi, wi, ho, wo, _stream()), "resize_bilinear")
+    with _timed("resize_bilinear", 1):
+        _check(lib().adamvs_resize_bilinear_f32(_p(x), _p(out), n, hi, wi, ho, wo, _stream()), "resize_bilinear")
     return out
 
 
@@ -152,8 +192,9 @@ def fused_volume(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, weights: t
     assert tuple(weights.shape) == (B, V - 1, h, w), (weights.shape, (B, V - 1, h, w))
     if out is None:
         out = torch.empty((B, C, D, h, w), device=feat.device, dtype=torch.float32)
-    _check(lib().adamvs_fused_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(weights), eps_mode,
-                                         _p(out), B, V, C, D, h, w, _stream()), "fused_volume")
+    with _timed("fused_volume", 1):
+        _check(lib().adamvs_fused_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(weights), eps_mode,
+                                             _p(out), B, V, C, D, h, w, _stream()), "fused_volume")
     return out
 
 
@@ -176,9 +217,10 @@ def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob
     logits = torch.empty((B, D, Ho, Wo), device=volume.device, dtype=torch.float32) if want_logits else None
     keep = {k: _f32c(v, k) for k, v in weights.items()}
     st = RegnetWeights(**{k: v.data_ptr() for k, v in keep.items()})
-    _check(lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
-                                       _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
-                                       B, C, D, h, w, _stream()), "regnet_red")
+    with _timed("regnet_red", 7 + 8 * D):
+        _check(lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
+                                           _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
+                                           B, C, D, h, w, _stream()), "regnet_red")
     return (depth, conf, logits) if want_logits else (depth, conf)
 
 
@@ -188,6 +230,7 @@ def softmax_regress(logits: torch.Tensor, hyp: Hyp, prob_mode: int, n_per_batch:
     N, D, h, w = logits.shape
     depth = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
     conf = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
-    _check(lib().adamvs_softmax_regress_f32(_p(logits), *hyp.args(), prob_mode, _p(depth), _p(conf),
-                                            N, n_per_batch, D, h, w, _stream()), "softmax_regress")
+    with _timed("softmax_regress", 1):
+        _check(lib().adamvs_softmax_regress_f32(_p(logits), *hyp.args(), prob_mode, _p(depth), _p(conf),
+                                                N, n_per_batch, D, h, w, _stream()), "softmax_regress")
     return depth, conf

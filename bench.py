@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the Ada-MVS cascade hot path (BASELINE.json metric: depth maps/sec, 5-view 768x384).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one forward of the drop-in ``Infer_AdaMVSNet`` (predict_whu.py's class) over a batch of B
+reference views (1 ref + 4 src each, 3x384x768, ndepths 48/32/8, fp32) per GPU.  Views are
+independent, so N GPUs run N such batches with no data-path collective (weak scaling); NCCL is used
+only for the barrier and the max-over-ranks of the device time.
+
+Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e`` the same metric
+through the public forward() with pinned-host inputs and a device->host read of the results inside
+the timed region.  ``roofline`` is measured live with CUDA events around the fused cost-volume kernel
+(K2, HBM-bound — the kernel BASELINE.json's metric names); ``kernels`` lists every C-ABI kernel's share
+of the step and its own bound.  ``cpu_baseline`` / ``--impl reference`` time the oracle's CPU port of
+the reference (the reference itself is Python and does not travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, V = 384, 768, 5
+NDEPTHS = (48, 32, 8)
+RATIOS = (4.0, 2.0, 1.0)
+NUM_DEPTH = 192
+METRIC = "depth maps/sec, 5-view 768x384"
+UNIT = "depth_maps/s"
+WORKLOAD = ("configs[1]: Ada-MVS 5-view (1 ref + 4 src) 768x384 cascade inference, fp32, random-init weights; "
+            "reference views are independent and are sharded over ranks (configs[2])")
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def costvolume_algorithmic_bytes(B, C, D, h, w, Vs=4):
+    """every feature map read once, hypothesis source and weights read once,
+    the aggregated volume written once (fp32)."""
+    return 4 * B * ((1 + Vs) * C * h * w + h * w + Vs * h * w + C * D * h * w)
+
+
+def regnet_flops(B, C, D, h, w):
+    """Conv FLOPs of one recurrent-regulariser sweep (2*9*Cin*Cout per output pixel; transposed
+    convs per input pixel)."""
+    full, half = h * w, (h // 2) * (w // 2)
+    per_plane = 18 * (C * 8 * full + 16 * 16 * full + 16 * 8 * full + 8 * 16 * half + 32 * 32 * half
+                      + 32 * 16 * half + 16 * 8 * half + 8 * 1 * full)
+    return B * D * per_plane
+
+
+class ClockSampler:
+    """nvidia-smi sampler running for the duration of the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_maps_per_s(n_maps=3, warmup=1):
+    """The oracle's CPU port of Infer_AdaMVSNet.forward, all host threads, B=1 (reference's own batch size)."""
+    import torch
+    from adamvs_b200 import synth
+    from oracle import adamvs_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs, proj, dv = synth.make_sample(1, H, W, V, seed=0)
+    sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
+    f = O.feature_net(sd, imgs[:, 0])
+    sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+    times = []
+    for i in range(warmup + n_maps):
+        t0 = time.perf_counter()
+        O.infer_adamvs_forward(sd, imgs, proj, dv, num_depth=NUM_DEPTH, ndepths=NDEPTHS, ratios=RATIOS)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return 1.0 / statistics.median(times), torch.get_num_threads(), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    steps = min(steps, 10)                                   # bounded sample: one depth map per step
+    mps, cores, times = cpu_reference_maps_per_s(n_maps=steps, warmup=min(warm, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warm, 2), "ms_per_step": 1e3 / mps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "class": "Infer_AdaMVSNet", "ndepths": list(NDEPTHS), "num_depth": NUM_DEPTH,
+                   "views": V, "arm": "oracle torch-CPU port of the reference's PyTorch path, B=1 per step (the "
+                                      "reference's own batch size), all host threads"},
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} depth maps (1 per step), median, after {min(warm, 2)} warm-up"},
+        "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("ADAMVS_BENCH_BATCH", "8")),
+                    help="reference views per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from adamvs_b200 import ops, synth
+    from models.adamvs import Infer_AdaMVSNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    min_warm = 1 if os.environ.get("ADAMVS_BENCH_PROFILING") else 3      # profiler passes only; never a bench value
+    steps, warm, B = max(1, args.steps), max(min_warm, args.warmup), max(1, args.batch)
+
+    # ---- model: seeded random-init weights, calibrated so that probabilities are not uniform
+    with open(os.devnull, "w") as devnull:
+        stdout, sys.stdout = sys.stdout, devnull
+        try:
+            model = Infer_AdaMVSNet(num_depth=NUM_DEPTH, ndepths=list(NDEPTHS), depth_intervals_ratio=list(RATIOS))
+        finally:
+            sys.stdout = stdout
+    sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    NSETS = 3                                                # distinct input batches, cycled (not L2-hot)
+    host = []
+    for s in range(NSETS):
+        imgs, proj, dv = synth.make_sample(B, H, W, V, seed=1 + rank * NSETS + s)
+        host.append((imgs.pin_memory(), {k: v.pin_memory() for k, v in proj.items()}, dv.pin_memory()))
+    with torch.no_grad():
+        f = model.feature(host[0][0][:1, 0].to(dev))
+    sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+    model.load_state_dict(sd)
+    resident = [(i.to(dev), {k: v.to(dev) for k, v in p.items()}, d.to(dev)) for i, p, d in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        imgs, proj, dv = resident[i % NSETS]
+        return model(imgs, proj, dv)
+
+    out_host = [torch.empty((B, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def step_e2e(i):
+        imgs, proj, dv = host[i % NSETS]
+        out = model(imgs.to(dev, non_blocking=True), {k: v.to(dev, non_blocking=True) for k, v in proj.items()},
+                    dv.to(dev, non_blocking=True))
+        out_host[0].copy_(out["depth"], non_blocking=True)
+        out_host[1].copy_(out["photometric_confidence"], non_blocking=True)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for i in range(warm):
+            step_resident(i)
+        # ---- timed region 1: device-resident inputs, per-kernel CUDA-event timers on, clocks sampled
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        timing = {}
+        ops.set_timing(timing)
+        ops.LAUNCHES[0] = 0
+        ms_total = timed(step_resident, steps)
+        launches = ops.LAUNCHES[0]
+        ops.set_timing(None)
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- timed region 2: end to end through forward() with pinned-host inputs and D2H of the result
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e = timed(step_e2e, steps)
+
+    maps = world * B * steps
+    value = maps / (ms_total * 1e-3)
+    e2e_value = maps / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel accounting (rank 0): mean device time per launch from the CUDA events
+    hbm_peak, tensor_peak, peak_src = _peaks()
+    ffma_peak = 56.3                                         # TFLOP/s, tools/ffma_probe.cu on this pool (profiles/r01_ffma_probe.txt)
+    per_kernel = {}
+    for name, evs in timing.items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        per_kernel[name] = {"launches": len(ms), "ms_mean": sum(ms) / len(ms), "ms_total": sum(ms)}
+    step_ms = ms_total / steps
+    shapes = {"stage1": (32, 48, H // 4, W // 4), "stage2": (16, 32, H // 2, W // 2), "stage3": (8, 8, H, W)}
+    kernels = {}
+    for name, st in per_kernel.items():
+        entry = {"ms_per_step": st["ms_total"] / steps, "share_of_step": st["ms_total"] / steps / step_ms}
+        stage = name.split("/")[-1]
+        if name.startswith("fused_volume/"):
+            C, D, h, w = shapes[stage]
+            by = costvolume_algorithmic_bytes(B, C, D, h, w)
+            entry.update({"bound": "hbm", "algorithmic_bytes": by, "achieved_GBps": by / st["ms_mean"] * 1e-6,
+                          "frac_of_hbm_peak": by / st["ms_mean"] * 1e-6 / hbm_peak})
+        elif name.startswith("regnet_red/"):
+            C, D, h, w = shapes[stage]
+            fl = regnet_flops(B, C, D, h, w)
+            entry.update({"bound": "fp32 FFMA (fp32 parity forbids tf32/bf16 operands)", "flops": fl,
+                          "achieved_TFLOPs": fl / st["ms_mean"] * 1e-9,
+                          "frac_of_ffma_peak": fl / st["ms_mean"] * 1e-9 / ffma_peak,
+                          "frac_of_bf16_tensor_peak": fl / st["ms_mean"] * 1e-9 / tensor_peak})
+        kernels[name] = entry
+    # headline roofline: the fused warp + cost-volume kernel with the largest launch (stage 2)
+    dom = max((k for k in kernels if k.startswith("fused_volume/")), key=lambda k: kernels[k]["algorithmic_bytes"])
+    roofline = {"kernel": "fused_volume_kernel (K2) " + dom.split("/")[-1], "bound": "hbm",
+                "achieved": kernels[dom]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"]}
+    traffic_file = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                t = json.load(fh)
+            if int(t.get("batch", -1)) == B:
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = t.get("source")
+        except Exception:
+            pass
+
+    h2d = sum(t.numel() * t.element_size() for t in (host[0][0], host[0][2])) + \
+        sum(v.numel() * v.element_size() for v in host[0][1].values())
+    d2h = 2 * B * H * W * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "class": "Infer_AdaMVSNet", "ndepths": list(NDEPTHS), "num_depth": NUM_DEPTH,
+                   "views": V, "batch_per_gpu_per_step": B,
+                   "weights": "seeded random init, calibrated (SURVEY A.6)",
+                   "l2": f"{NSETS} distinct input batches cycled; >1 GB of cost volume written/read per step (>> 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        mps, cores, times = cpu_reference_maps_per_s(n_maps=3, warmup=1)
+        line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "3 depth maps (B=1, same 5-view 768x384 workload), median, after 1 warm-up; "
+                                          "oracle torch-CPU port of Infer_AdaMVSNet.forward"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
