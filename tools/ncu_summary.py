@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/X_launches.csv  > profiles/rNN_launches.txt
+    python tools/ncu_summary.py full     gpurun_out/X.ncu-rep       > profiles/rNN_X.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+FULL_METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+]
+
+
+def _to_ns(value, unit):
+    v = float(value.replace(",", ""))
+    return v * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
+
+
+def launches(path):
+    rows = list(csv.reader(open(path, newline="")))
+    hdr = None
+    agg = collections.OrderedDict()
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            if d.get("Metric Name") != "gpu__time_duration.sum":
+                continue
+            name = d["Kernel Name"]
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += _to_ns(d["Metric Value"], d["Metric Unit"])
+    tot = sum(v[1] for v in agg.values())
+    n = sum(v[0] for v in agg.values())
+    print(f"# {path}: {n} launches, {tot / 1e6:.3f} ms of kernel time (ncu: cold-cache, serialised - compare shares)")
+    print(f"# {'ms':>9s} {'launches':>8s} {'share':>6s} {'us/launch':>9s}  kernel")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1] / 1e6:11.3f} {v[0]:8d} {100 * v[1] / tot:5.1f}% {v[1] / v[0] / 1e3:9.2f}  {k[:150]}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# {path}: {len(data)} profiled launches (ncu --set full --clock-control none)")
+    for r in data:
+        print("=" * 100)
+        print(r[idx["Kernel Name"]][:160])
+        for m in FULL_METRICS:
+            if m in idx:
+                print(f"  {m:82s} {r[idx[m]]:>16s} {units[idx[m]]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
