@@ -37,7 +37,35 @@ class _ConvBN(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
 
     def forward(self, x):
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        if self.training or not _FOLD_BN:
+            return F.relu(self.bn(self.conv(x)), inplace=True)
+        w, b = _folded(self.conv, self.bn)
+        c = self.conv
+        if isinstance(c, nn.ConvTranspose2d):
+            y = F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation)
+        else:
+            y = F.conv2d(x, w, b, c.stride, c.padding, c.dilation, c.groups)
+        return F.relu_(y)
+
+
+_FOLD_BN = True      # eval-mode BatchNorm is an affine map: fold it into the preceding bias-free conv
+
+
+def _folded(conv, bn):
+    """(weight, bias) of conv followed by eval-mode BatchNorm, cached on the conv module and rebuilt
+    whenever any of the five tensors involved is modified or moved."""
+    src = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in src)
+    cache = conv.__dict__.get("_adamvs_folded")
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            shape = (1, -1, 1, 1) if isinstance(conv, nn.ConvTranspose2d) else (-1, 1, 1, 1)
+            w = (conv.weight * scale.reshape(shape)).contiguous()
+            b = (bn.bias - bn.running_mean * scale).contiguous()
+        cache = (key, w, b)
+        conv.__dict__["_adamvs_folded"] = cache
+    return cache[1], cache[2]
 
 
 class _UpFuse(nn.Module):
@@ -114,14 +142,21 @@ class CostRegNet2D(nn.Module):
                 nn.BatchNorm2d(n), nn.ReLU(inplace=True)))
         self.prob = nn.Conv2d(n, n, 3, stride=1, padding=1)
 
+    def _up(self, seq, x):
+        if self.training or not _FOLD_BN:
+            return seq(x)
+        c = seq[0]
+        w, b = _folded(c, seq[1])
+        return F.relu_(F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation))
+
     def forward(self, x):
         e0 = self.conv0(x)
         e2 = self.conv2(self.conv1(e0))
         e4 = self.conv4(self.conv3(e2))
         y = self.conv6(self.conv5(e4))
-        y = e4 + self.conv7(y)
-        y = e2 + self.conv9(y)
-        y = e0 + self.conv11(y)
+        y = e4 + self._up(self.conv7, y)
+        y = e2 + self._up(self.conv9, y)
+        y = e0 + self._up(self.conv11, y)
         return self.prob(y)
 
 
