@@ -6,6 +6,8 @@
 // Thread mapping: one thread per (reference pixel, depth plane), x fastest, channels innermost with
 // the tap sets of all source views held in registers.
 #include "common.cuh"
+#include "tma.cuh"
+#include <limits.h>
 
 namespace adamvs {
 
@@ -145,6 +147,299 @@ static int launch_fused_volume(const float* feat, const float* relproj, const Hy
     ADAMVS_LAUNCH_RESULT();
 }
 
+// ================================================================================================
+// TMA-staged variant (the fast path; needs w % 4 == 0).
+//
+// A block owns a 32x8 pixel tile and KC = 4 adjacent depth planes of one batch item.  Every thread
+// first computes the bilinear cells and weights of its pixel for the 4 planes x VS views; a block-wide
+// min/max gives, per source view, the bounding box of all cells.  When every box fits BW x BH texels
+// (always for the near-fronto-parallel geometry of aerial blocks; otherwise the block takes the
+// global-gather path below) the source footprint is brought into shared memory by the TMA unit,
+// 4 channels x VS views per stage, double buffered: out-of-image texels arrive as zeros, which is
+// exactly grid_sample's per-corner zero padding, so taps need no clamping or masking.  The gather
+// then is `LDS [cell + immediate]` (no address arithmetic per tap): 16 LDS + 16 FFMA per output.
+// The binding resource is the shared-memory gather rate (16 taps x 4 B per 4-byte output at
+// 128 B/clk/SM), not HBM: DESIGN.md §3.
+// ================================================================================================
+constexpr int kBW = 48, kBH = 12;          // source box per (view, channel): width (multiple of 4), height
+constexpr int kBox = kBW * kBH;
+constexpr int kCK = 4;                      // channels per pipeline stage
+constexpr int kKC = 4;                      // depth planes per block
+constexpr int kPX = 32, kPY = 8;            // pixel tile
+constexpr int kWvThreads = kPX * kPY;
+
+enum { MODE_FUSED = 0, MODE_SCORE = 1, MODE_VARIANCE = 2 };
+
+struct WarpVolArgs {
+    const float* feat;        // [B,V,C,h,w]
+    const float* relproj;     // [B,V-1,12]
+    HypSpec hs;
+    const float* weights;     // MODE_FUSED: [B,V-1,h,w]
+    int eps_mode;
+    float* out;               // FUSED/VARIANCE: [B,C,D,h,w]; SCORE: [B,V-1,D,h,w]
+    int D, h, w;
+};
+
+// Unclamped bilinear cell (x0,y0 may be -1) and corner weights; false when the sample lies entirely
+// outside the source image, behind the camera or is not finite (contributes zero).
+__device__ __forceinline__ bool cell_taps(const Ray& r, float d, int h, int w, float scale, int& x0, int& y0, float (&wt)[4]) {
+    const float X = __fadd_rn(__fmul_rn(r.qx, d), r.tx);
+    const float Y = __fadd_rn(__fmul_rn(r.qy, d), r.ty);
+    const float Z = __fadd_rn(__fmul_rn(r.qz, d), r.tz);
+    const float rz = __frcp_rn(Z);                     // one correctly rounded reciprocal instead of two divisions:
+    const float u = __fmul_rn(X, rz);                  // <= 1.5 ulp on u, v (6e-5 px at u ~ 700), below the reference's own
+    const float v = __fmul_rn(Y, rz);                  // normalise / un-normalise round trip
+    const bool ok = (Z > 0.f) && (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);
+    const float fu = floorf(ok ? u : 0.f), fv = floorf(ok ? v : 0.f);
+    x0 = (int)fu; y0 = (int)fv;
+    const float ax = (ok ? u : 0.f) - fu, ay = (ok ? v : 0.f) - fv;
+    const float bx = 1.f - ax, by = 1.f - ay;
+    const float sc = ok ? scale : 0.f;
+    wt[0] = bx * by * sc; wt[1] = ax * by * sc; wt[2] = bx * ay * sc; wt[3] = ax * ay * sc;
+    return ok;
+}
+
+// Global-gather path for one pixel and the block's planes (any geometry).  Same arithmetic as the
+// fast path; used by blocks whose source footprint does not fit the shared-memory box.
+template <int C, int VS, int MODE>
+__device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x, int y, int k0) {
+    constexpr int V = VS + 1;
+    const int hw = a.h * a.w, pix = y * a.w + x;
+    const float* ref = a.feat + ((size_t)b * V) * C * hw + pix;
+    const float* src0 = a.feat + ((size_t)b * V + 1) * C * hw;
+    const HypLine line = hyp_line(a.hs, b, pix, hw, a.D);
+    float wv[VS], wsum = 0.f;
+#pragma unroll
+    for (int v = 0; v < VS; ++v) {
+        wv[v] = MODE == MODE_FUSED ? __ldg(a.weights + ((size_t)b * VS + v) * hw + pix) : 1.f;
+        wsum += wv[v];
+    }
+    const bool eps_num = (a.eps_mode == ADAMVS_EPS_NUMERATOR);
+    const float inv = 1.f / (eps_num ? wsum : (1e-5f + wsum));
+    const float start = eps_num ? 1e-5f : 0.f;
+    for (int kk = 0; kk < kKC; ++kk) {
+        const int k = k0 + kk;
+        if (k >= a.D) break;
+        const float d = hyp_at(line, k);
+        WTaps t[VS];
+#pragma unroll
+        for (int v = 0; v < VS; ++v)
+            t[v] = scaled_taps(make_ray(a.relproj + ((size_t)b * VS + v) * 12, (float)x, (float)y), d, a.h, a.w, wv[v]);
+        float acc[VS];
+#pragma unroll
+        for (int v = 0; v < VS; ++v) acc[v] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float rc = __ldg(ref + (size_t)c * hw);
+            if (MODE == MODE_FUSED) {
+                float s = 0.f;
+#pragma unroll
+                for (int v = 0; v < VS; ++v) s = gather4(src0 + ((size_t)v * C + c) * hw, t[v], s);
+                __stcs(a.out + (((size_t)b * C + c) * a.D + k) * hw + pix, fmaf(rc, s, start) * inv);
+            } else if (MODE == MODE_SCORE) {
+#pragma unroll
+                for (int v = 0; v < VS; ++v) acc[v] = fmaf(rc, gather4(src0 + ((size_t)v * C + c) * hw, t[v], 0.f), acc[v]);
+            } else {
+                float sum = rc, sq = rc * rc;
+#pragma unroll
+                for (int v = 0; v < VS; ++v) {
+                    const float sv = gather4(src0 + ((size_t)v * C + c) * hw, t[v], 0.f);
+                    sum += sv; sq = fmaf(sv, sv, sq);
+                }
+                const float m = sum / (float)V;
+                __stcs(a.out + (((size_t)b * C + c) * a.D + k) * hw + pix, sq / (float)V - m * m);
+            }
+        }
+        if (MODE == MODE_SCORE) {
+#pragma unroll
+            for (int v = 0; v < VS; ++v) a.out[(((size_t)b * VS + v) * a.D + k) * hw + pix] = acc[v] / (float)C;
+        }
+    }
+}
+
+template <int C, int VS, int MODE>
+__global__ void __launch_bounds__(kWvThreads, 2)
+warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, int nk) {
+    constexpr int V = VS + 1;
+    constexpr int NCH = C / kCK;
+    constexpr int STAGE = VS * kCK * kBox;             // floats per pipeline stage
+    static_assert(C % kCK == 0, "channel count must be a multiple of the stage depth");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sbuf = reinterpret_cast<float*>(smem_raw);                  // [2][VS][kCK][kBH][kBW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbuf + 2 * STAGE);    // [2]
+    int* sbox = reinterpret_cast<int*>(bars + 2);                      // [VS][4] minx, miny, maxx, maxy
+
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    const int kchunk = blockIdx.x % nk, tile = blockIdx.x / nk;        // plane chunk fastest: blocks that share a
+    const int tiles_x = (a.w + kPX - 1) / kPX;                         // source footprint run together (L2 hits)
+    const int x = (tile % tiles_x) * kPX + lane, y = (tile / tiles_x) * kPY + row;
+    const int b = blockIdx.y;
+    const int k0 = kchunk * kKC;
+    const int hw = a.h * a.w;
+    const bool inside = (x < a.w) && (y < a.h);
+    const int pix = inside ? y * a.w + x : 0;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (tid < VS * 4) sbox[tid] = (tid & 2) ? INT_MIN : INT_MAX;
+    __syncthreads();
+
+    // ---- phase 1: cells + weights of this pixel for kKC planes x VS views; bounding boxes
+    float wt[kKC][VS][4];
+    int cell[kKC][VS];                   // (y0+1) << 16 | (x0+1); later the box-relative float offset
+    float inv = 0.f, start = 0.f;
+    {
+        const HypLine line = hyp_line(a.hs, b, pix, hw, a.D);
+        float wsum = 0.f;
+#pragma unroll
+        for (int v = 0; v < VS; ++v) {
+            const float wv = (MODE == MODE_FUSED && inside) ? __ldg(a.weights + ((size_t)b * VS + v) * hw + pix) : 1.f;
+            wsum += wv;
+            const Ray ray = make_ray(a.relproj + ((size_t)b * VS + v) * 12, (float)x, (float)y);
+            int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+#pragma unroll
+            for (int kk = 0; kk < kKC; ++kk) {
+                int x0, y0;
+                const bool ok = cell_taps(ray, hyp_at(line, k0 + kk), a.h, a.w, wv, x0, y0, wt[kk][v]) && inside && (k0 + kk < a.D);
+                if (ok) { mnx = min(mnx, x0); mxx = max(mxx, x0); mny = min(mny, y0); mxy = max(mxy, y0); }
+                else { x0 = INT_MAX; wt[kk][v][0] = wt[kk][v][1] = wt[kk][v][2] = wt[kk][v][3] = 0.f; }
+                cell[kk][v] = ok ? (((y0 + 1) << 16) | (x0 + 1)) : -1;
+            }
+            mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+            mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+            if (lane == 0) {
+                atomicMin(&sbox[v * 4 + 0], mnx); atomicMin(&sbox[v * 4 + 1], mny);
+                atomicMax(&sbox[v * 4 + 2], mxx); atomicMax(&sbox[v * 4 + 3], mxy);
+            }
+        }
+        const bool eps_num = (a.eps_mode == ADAMVS_EPS_NUMERATOR);
+        inv = 1.f / (eps_num ? wsum : (1e-5f + wsum));
+        start = eps_num ? 1e-5f : 0.f;
+    }
+    __syncthreads();
+    int bx[VS], by[VS];
+    bool fits = true;
+#pragma unroll
+    for (int v = 0; v < VS; ++v) {
+        const int mnx = sbox[v * 4 + 0], mny = sbox[v * 4 + 1], mxx = sbox[v * 4 + 2], mxy = sbox[v * 4 + 3];
+        const bool any = mnx != INT_MAX;
+        bx[v] = any ? (mnx & ~3) : 0;                  // TMA: innermost start coordinate 16-byte aligned
+        by[v] = any ? mny : 0;
+        fits = fits && (!any || ((mxx + 1 - bx[v] < kBW) && (mxy + 1 - by[v] < kBH)));
+    }
+    if (!fits) {                                       // block-uniform
+        if (inside) warp_volume_slow<C, VS, MODE>(a, b, x, y, k0);
+        return;
+    }
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk)
+#pragma unroll
+        for (int v = 0; v < VS; ++v) {
+            const int c = cell[kk][v];
+            cell[kk][v] = c < 0 ? 0 : (((c >> 16) - 1 - by[v]) * kBW + ((c & 0xffff) - 1 - bx[v]));
+        }
+
+    // ---- phase 2: double-buffered channel stages
+    auto issue = [&](int ch) {
+        const int s = ch & 1;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[s], STAGE * 4);
+#pragma unroll
+        for (int v = 0; v < VS; ++v)
+            tma_load_4d(sbuf + s * STAGE + v * kCK * kBox, &tm, &bars[s], bx[v], by[v], 0, (b * V + v + 1) * C + ch * kCK);
+    };
+    if (tid == 0) issue(0);
+    const float* ref = a.feat + ((size_t)b * V) * C * hw + pix;
+    float acc[MODE == MODE_SCORE ? kKC : 1][MODE == MODE_SCORE ? VS : 1];
+    if (MODE == MODE_SCORE) {
+#pragma unroll
+        for (int kk = 0; kk < kKC; ++kk)
+#pragma unroll
+            for (int v = 0; v < VS; ++v) acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] = 0.f;
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int s = ch & 1;
+        if (tid == 0 && ch + 1 < NCH) issue(ch + 1);
+        float rc[kCK];
+#pragma unroll
+        for (int cc = 0; cc < kCK; ++cc) rc[cc] = inside ? __ldg(ref + (size_t)(ch * kCK + cc) * hw) : 0.f;
+        mbar_wait(&bars[s], (ch >> 1) & 1);
+        const float* st = sbuf + s * STAGE;
+#pragma unroll
+        for (int cc = 0; cc < kCK; ++cc) {
+#pragma unroll
+            for (int kk = 0; kk < kKC; ++kk) {
+                float sum = rc[cc], sq = rc[cc] * rc[cc], sacc = 0.f;
+#pragma unroll
+                for (int v = 0; v < VS; ++v) {
+                    const float* p = st + (v * kCK + cc) * kBox + cell[kk][v];
+                    float sv = MODE == MODE_FUSED ? sacc : 0.f;
+                    sv = fmaf(wt[kk][v][0], p[0], sv);
+                    sv = fmaf(wt[kk][v][1], p[1], sv);
+                    sv = fmaf(wt[kk][v][2], p[kBW], sv);
+                    sv = fmaf(wt[kk][v][3], p[kBW + 1], sv);
+                    if (MODE == MODE_FUSED) sacc = sv;
+                    else if (MODE == MODE_SCORE) acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] =
+                        fmaf(rc[cc], sv, acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0]);
+                    else { sum += sv; sq = fmaf(sv, sv, sq); }
+                }
+                if (MODE != MODE_SCORE && inside && k0 + kk < a.D) {
+                    float r;
+                    if (MODE == MODE_FUSED) r = fmaf(rc[cc], sacc, start) * inv;
+                    else { const float m = sum / (float)V; r = sq / (float)V - m * m; }
+                    __stcs(a.out + (((size_t)b * C + ch * kCK + cc) * a.D + k0 + kk) * hw + pix, r);
+                }
+            }
+        }
+        __syncthreads();                               // stage s fully consumed before chunk ch+2 lands in it
+    }
+    if (MODE == MODE_SCORE && inside) {
+#pragma unroll
+        for (int kk = 0; kk < kKC; ++kk)
+#pragma unroll
+            for (int v = 0; v < VS; ++v)
+                if (k0 + kk < a.D)
+                    a.out[(((size_t)b * VS + v) * a.D + k0 + kk) * hw + pix] =
+                        acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] / (float)C;
+    }
+}
+
+template <int C, int VS, int MODE>
+static int launch_warp_volume_tma(const WarpVolArgs& a, int B, cudaStream_t st) {
+    constexpr size_t smem = sizeof(float) * 2 * VS * kCK * kBox + 2 * sizeof(uint64_t) + VS * 4 * sizeof(int);
+    CUtensorMap tm;
+    if (!make_tmap_4d(&tm, a.feat, a.w, a.h, 1, (long long)B * (VS + 1) * C, kBW, kBH, kCK)) return -100;
+    auto kern = warp_volume_tma_kernel<C, VS, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int nk = (a.D + kKC - 1) / kKC;
+    const long long tiles = (long long)((a.w + kPX - 1) / kPX) * ((a.h + kPY - 1) / kPY);
+    if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
+    dim3 grid((unsigned)(tiles * nk), B, 1);
+    kern<<<grid, kWvThreads, smem, st>>>(tm, a, nk);
+    ADAMVS_LAUNCH_RESULT();
+}
+
+// TMA needs 16-byte aligned rows: w % 4 == 0 and a 16-byte aligned base; C a multiple of the stage depth.
+static bool tma_eligible(const float* feat, int w, int h) {
+    return (w % 4 == 0) && (reinterpret_cast<uintptr_t>(feat) % 16 == 0) && h < 65535 && w < 65535;
+}
+
+template <int MODE>
+static int dispatch_warp_volume_tma(const WarpVolArgs& a, int B, int V, int C, cudaStream_t st) {
+#define ADAMVS_WV(CC, VV) return launch_warp_volume_tma<CC, VV, MODE>(a, B, st)
+#define ADAMVS_WV_C(VV) switch (C) { case 8: ADAMVS_WV(8, VV); case 16: ADAMVS_WV(16, VV); case 32: ADAMVS_WV(32, VV); default: return -100; }
+    switch (V - 1) {
+        case 2: ADAMVS_WV_C(2)
+        case 3: ADAMVS_WV_C(3)
+        case 4: ADAMVS_WV_C(4)
+        case 5: ADAMVS_WV_C(5)
+        case 6: ADAMVS_WV_C(6)
+        default: return -100;                          // other view counts: global-gather kernels
+    }
+#undef ADAMVS_WV_C
+#undef ADAMVS_WV
+}
+
 static int check_hyp(int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range) {
     if (!hyp_src) return ADAMVS_EINVAL;
     if (hyp_mode == ADAMVS_HYP_PLANES) return hyp_ncol >= 2 ? 0 : ADAMVS_EINVAL;
@@ -164,6 +459,11 @@ extern "C" int adamvs_pair_score_f32(const float* feat, const float* relproj,
     if (int e = check_hyp(hyp_mode, hyp_src, hyp_ncol, half_range)) return e;
     const HypSpec hs{hyp_mode, hyp_src, hyp_ncol, half_range};
     cudaStream_t st = (cudaStream_t)stream;
+    if (tma_eligible(feat, w, h)) {
+        const WarpVolArgs a{feat, relproj, hs, nullptr, ADAMVS_EPS_DENOMINATOR, score, D, h, w};
+        const int rc = dispatch_warp_volume_tma<MODE_SCORE>(a, B, V, C, st);
+        if (rc != -100) return rc;
+    }
     switch (C) {
         case 8:  return launch_pair_score<8>(feat, relproj, hs, score, B, V, D, h, w, st);
         case 16: return launch_pair_score<16>(feat, relproj, hs, score, B, V, D, h, w, st);
@@ -181,6 +481,11 @@ extern "C" int adamvs_fused_volume_f32(const float* feat, const float* relproj,
     if (int e = check_hyp(hyp_mode, hyp_src, hyp_ncol, half_range)) return e;
     const HypSpec hs{hyp_mode, hyp_src, hyp_ncol, half_range};
     cudaStream_t st = (cudaStream_t)stream;
+    if (tma_eligible(feat, w, h)) {
+        const WarpVolArgs a{feat, relproj, hs, weights, eps_mode, volume, D, h, w};
+        const int rc = dispatch_warp_volume_tma<MODE_FUSED>(a, B, V, C, st);
+        if (rc != -100) return rc;
+    }
 #define ADAMVS_FV(CC, VV) return launch_fused_volume<CC, VV>(feat, relproj, hs, weights, eps_mode, volume, B, D, h, w, st)
 #define ADAMVS_FV_C(VV) switch (C) { case 8: ADAMVS_FV(8, VV); case 16: ADAMVS_FV(16, VV); case 32: ADAMVS_FV(32, VV); default: return ADAMVS_EINVAL; }
     switch (V - 1) {

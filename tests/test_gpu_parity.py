@@ -111,6 +111,41 @@ def test_pair_score_and_fused_volume_vs_oracle(C, D, h, w):
             assert abs_err(got, want) < 2e-4 * float(want.abs().max()), (mode, eps_mode)
 
 
+@pytest.mark.parametrize("case", ["zoom", "rot90", "w_not_mult4"])
+def test_cost_volume_fallback_paths_vs_oracle(case):
+    """Geometries whose source footprint does not fit the shared-memory box (x2.2 zoom, 90 degree roll)
+    take the in-kernel global-gather path; widths that are not a multiple of 4 take the non-TMA kernels.
+    All must agree with the oracle like the staged path does."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    B, V, C, D = 1, 5, 8, 6
+    h, w = (40, 64) if case != "w_not_mult4" else (30, 50)
+    g = torch.Generator().manual_seed(17)
+    feat = torch.randn(B, V, C, h, w, generator=g)
+    proj = synth.make_cameras(h, w, V - 1)["stage3"].unsqueeze(0).clone()
+    if case == "zoom":
+        proj[0, 1:, :2, :] *= 2.2                                      # source focal length and principal point x2.2
+    elif case == "rot90":
+        rz = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+        K = torch.tensor([[1.2 * w, 0, w / 2.0], [0, 1.2 * w, h / 2.0], [0, 0, 1.0]])
+        for v in (1, 3):
+            proj[0, v, :3, :] = K @ rz @ torch.linalg.inv(K) @ proj[0, v, :3, :]
+    dv = torch.tensor([[520.0, 680.0]])
+    wts = torch.rand(B, V - 1, h, w, generator=g) * 0.9 + 0.05
+    relproj, _ = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 192, [D] * 3, [1.0] * 3)
+    hyp = ops.Hyp(ops.HYP_PLANES, dv.to(_dev()))
+    hyps = O.depth_hypotheses(dv, D, 0.0, [B, h, w])
+    prods = [feat[:, 0].unsqueeze(2) * O.homography_warp(feat[:, v], proj[:, v], proj[:, 0], hyps) for v in range(1, V)]
+    score_want = torch.stack([p.mean(1) for p in prods], 1)
+    score = ops.pair_score(feat.to(_dev()), relproj[0], hyp, D).cpu()
+    assert abs_err(score, score_want) < 2e-4 * float(score_want.abs().max())
+    num = sum(p * wts[:, v].unsqueeze(1).unsqueeze(1) for v, p in enumerate(prods))
+    want = num / (1e-5 + wts.sum(1).unsqueeze(1).unsqueeze(1))
+    got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, wts.to(_dev()), ops.EPS_DENOMINATOR, D).cpu()
+    assert float(want.abs().max()) > 0.1
+    assert abs_err(got, want) < 2e-4 * float(want.abs().max())
+
+
 def test_fused_volume_zero_padding_and_behind_camera():
     """Out-of-image taps contribute zero per corner (grid_sample zeros padding); Z<=0 gives zeros."""
     ops = _ops()
