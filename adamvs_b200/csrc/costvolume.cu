@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "tma.cuh"
 #include <limits.h>
+#include <type_traits>
 
 namespace adamvs {
 
@@ -161,7 +162,11 @@ static int launch_fused_volume(const float* feat, const float* relproj, const Hy
 // The binding resource is the shared-memory gather rate (16 taps x 4 B per 4-byte output at
 // 128 B/clk/SM), not HBM: DESIGN.md §3.
 // ================================================================================================
-constexpr int kBW = 48, kBH = 12;          // source box per (view, channel): width (multiple of 4), height
+constexpr int kBW = 64, kBH = 12;          // source box per (view, channel).  The row pitch is a multiple of the 32
+                                            // banks, so a warp (32 consecutive x) stays conflict free when a slight
+                                            // rotation makes it straddle two source rows.  What remains are wrap-around
+                                            // conflicts when the source magnification exceeds 1 (32 lanes then span 33
+                                            // words); a 16x2 warp shape with pitch 48 measured no better (profiles/r01f).
 constexpr int kBox = kBW * kBH;
 constexpr int kCK = 4;                      // channels per pipeline stage
 constexpr int kKC = 4;                      // depth planes per block
@@ -169,6 +174,11 @@ constexpr int kPX = 32, kPY = 8;            // pixel tile
 constexpr int kWvThreads = kPX * kPY;
 
 enum { MODE_FUSED = 0, MODE_SCORE = 1, MODE_VARIANCE = 2 };
+
+// Predicated streaming store: keeps the gather loop free of branches (the value is always computed).
+__device__ __forceinline__ void st_cs_pred(float* p, float v, bool pred) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.cs.f32 [%0], %1; }" ::"l"(p), "f"(v), "r"((int)pred) : "memory");
+}
 
 struct WarpVolArgs {
     const float* feat;        // [B,V,C,h,w]
@@ -348,6 +358,12 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
     };
     if (tid == 0) issue(0);
     const float* ref = a.feat + ((size_t)b * V) * C * hw + pix;
+    // per-thread gather bases: every tap address below is base + compile-time constant (stage, view, channel, corner)
+    const float* tap[kKC][VS];
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk)
+#pragma unroll
+        for (int v = 0; v < VS; ++v) tap[kk][v] = sbuf + cell[kk][v];
     float acc[MODE == MODE_SCORE ? kKC : 1][MODE == MODE_SCORE ? VS : 1];
     if (MODE == MODE_SCORE) {
 #pragma unroll
@@ -355,49 +371,71 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
 #pragma unroll
             for (int v = 0; v < VS; ++v) acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] = 0.f;
     }
-#pragma unroll 1
-    for (int ch = 0; ch < NCH; ++ch) {
-        const int s = ch & 1;
+    const size_t plane_stride = (size_t)a.D * hw;      // output channel stride
+    float* outp = a.out + ((size_t)b * C * a.D + k0) * hw + pix;
+    bool kvalid[kKC];
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk) kvalid[kk] = inside && (k0 + kk < a.D);
+
+    auto stage_body = [&](auto stage_tag, int ch) {
+        constexpr int S = decltype(stage_tag)::value;
         if (tid == 0 && ch + 1 < NCH) issue(ch + 1);
         float rc[kCK];
 #pragma unroll
         for (int cc = 0; cc < kCK; ++cc) rc[cc] = inside ? __ldg(ref + (size_t)(ch * kCK + cc) * hw) : 0.f;
-        mbar_wait(&bars[s], (ch >> 1) & 1);
-        const float* st = sbuf + s * STAGE;
+        mbar_wait(&bars[S], (ch >> 1) & 1);
 #pragma unroll
         for (int cc = 0; cc < kCK; ++cc) {
 #pragma unroll
             for (int kk = 0; kk < kKC; ++kk) {
-                float sum = rc[cc], sq = rc[cc] * rc[cc], sacc = 0.f;
+                // one independent 4-tap chain per view (ILP), combined afterwards
+                float sv[VS];
 #pragma unroll
                 for (int v = 0; v < VS; ++v) {
-                    const float* p = st + (v * kCK + cc) * kBox + cell[kk][v];
-                    float sv = MODE == MODE_FUSED ? sacc : 0.f;
-                    sv = fmaf(wt[kk][v][0], p[0], sv);
-                    sv = fmaf(wt[kk][v][1], p[1], sv);
-                    sv = fmaf(wt[kk][v][2], p[kBW], sv);
-                    sv = fmaf(wt[kk][v][3], p[kBW + 1], sv);
-                    if (MODE == MODE_FUSED) sacc = sv;
-                    else if (MODE == MODE_SCORE) acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] =
-                        fmaf(rc[cc], sv, acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0]);
-                    else { sum += sv; sq = fmaf(sv, sv, sq); }
+                    const float* p = tap[kk][v] + (S * STAGE + (v * kCK + cc) * kBox);
+                    float t = wt[kk][v][0] * p[0];
+                    t = fmaf(wt[kk][v][1], p[1], t);
+                    t = fmaf(wt[kk][v][2], p[kBW], t);
+                    sv[v] = fmaf(wt[kk][v][3], p[kBW + 1], t);
                 }
-                if (MODE != MODE_SCORE && inside && k0 + kk < a.D) {
+                if (MODE == MODE_SCORE) {
+#pragma unroll
+                    for (int v = 0; v < VS; ++v)
+                        acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] =
+                            fmaf(rc[cc], sv[v], acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0]);
+                } else {
                     float r;
-                    if (MODE == MODE_FUSED) r = fmaf(rc[cc], sacc, start) * inv;
-                    else { const float m = sum / (float)V; r = sq / (float)V - m * m; }
-                    __stcs(a.out + (((size_t)b * C + ch * kCK + cc) * a.D + k0 + kk) * hw + pix, r);
+                    if (MODE == MODE_FUSED) {
+                        float sacc = sv[0];
+#pragma unroll
+                        for (int v = 1; v < VS; ++v) sacc += sv[v];
+                        r = fmaf(rc[cc], sacc, start) * inv;
+                    } else {
+                        float sum = rc[cc], sq = rc[cc] * rc[cc];
+#pragma unroll
+                        for (int v = 0; v < VS; ++v) { sum += sv[v]; sq = fmaf(sv[v], sv[v], sq); }
+                        const float m = sum / (float)V;
+                        r = sq / (float)V - m * m;
+                    }
+                    st_cs_pred(outp + (size_t)cc * plane_stride + (size_t)kk * hw, r, kvalid[kk]);
                 }
             }
         }
-        __syncthreads();                               // stage s fully consumed before chunk ch+2 lands in it
+        outp += (size_t)kCK * plane_stride;
+        __syncthreads();                               // stage S fully consumed before chunk ch+2 lands in it
+    };
+    static_assert(NCH % 2 == 0, "the stage loop is unrolled by the two pipeline buffers");
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ch += 2) {
+        stage_body(std::integral_constant<int, 0>{}, ch);
+        stage_body(std::integral_constant<int, 1>{}, ch + 1);
     }
-    if (MODE == MODE_SCORE && inside) {
+    if (MODE == MODE_SCORE) {
 #pragma unroll
         for (int kk = 0; kk < kKC; ++kk)
 #pragma unroll
             for (int v = 0; v < VS; ++v)
-                if (k0 + kk < a.D)
+                if (kvalid[kk])
                     a.out[(((size_t)b * VS + v) * a.D + k0 + kk) * hw + pix] =
                         acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] / (float)C;
     }
