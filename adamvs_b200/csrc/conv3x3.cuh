@@ -1,0 +1,542 @@
+// Register-tiled FFMA 3x3 convolutions (stride 1 / 2, two concatenated input tensors, fused epilogues) shared
+// by the Ada-MVS recurrent regulariser (regnet.cu) and the MS-REDNet regulariser (msrednet.cu).
+#pragma once
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace adamvs {
+
+
+constexpr int PX = 4;     // thread patch width  (pixels, along x)
+constexpr int PY = 2;     // thread patch height
+constexpr int COT = 8;    // output channels per thread
+constexpr int CK = 8;     // input channels staged per shared-memory chunk
+
+enum { EPI_RELU = 0, EPI_GATES = 1, EPI_CAND = 2, EPI_RAW_STATS = 3 };
+
+struct ConvArgs {
+    const float* inA; long long strideA_c, strideA_b;   // first  CA input channels: base, channel stride, batch stride
+    const float* inB; long long strideB_c, strideB_b;   // next   CB input channels
+    const float* wpk;      // packed weights [CIN][9][COUT]
+    const float* bias;     // [COUT] or nullptr
+    float* out0;           // RELU: out [B,COUT,hout,wout] | GATES: rh [B,HC,h,w] | CAND: h (read-modify-write)
+    float* out1;           // GATES: u [B,HC,h,w]
+    const float* hstate;   // GATES / CAND: h [B,HC,h,w]
+    const float* ugate;    // CAND: u [B,HC,h,w]
+    int hin, win, hout, wout;
+    int planesA, planesB;  // channels per batch item of the tensors behind inA / inB (TMA plane coordinate)
+    int k;                 // depth-plane coordinate of inA (conv1 reads plane k of the cost volume)
+    double* stats;         // RAW_STATS: [B][2][2] = per batch item, per channel half, {sum, sum of squares}
+    int stats_split;       // RAW_STATS: 1 = two halves of COUT are separate groups (gate conv), 0 = one group
+};
+
+template <int STRIDE, int TW, int TH>
+struct TileGeom {
+    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
+    static constexpr int IW = STRIDE == 1 ? TW + 2 : 2 * TW + 1;
+    static constexpr int IP = STRIDE == 1 ? TW + 4 : 2 * TW + 4;     // row pitch, multiple of 4 floats
+    static constexpr int GROUP = (TW / PX) * (TH / PY);              // threads per output-channel group
+};
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TW, int TH>
+__global__ void __launch_bounds__((TW / PX) * (TH / PY) * (COB / COT))
+conv3x3_kernel(ConvArgs a) {
+    using G = TileGeom<STRIDE, TW, TH>;
+    constexpr int CIN = CA + CB;
+    constexpr int NT = G::GROUP * (COB / COT);
+    static_assert(CA % CK == 0 && CB % CK == 0, "channel groups must be chunk aligned");
+    static_assert(COB % COT == 0 && COUT % COB == 0, "bad output channel blocking");
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                                  // [CIN][9][COB]
+    float* sIn = smem + CIN * 9 * COB;                 // [CK][IH][IP]
+
+    const int tid = threadIdx.x;
+    const int cog = tid / G::GROUP;                    // output-channel group inside the block
+    const int t = tid - cog * G::GROUP;
+    const int tx = t % (TW / PX), ty = t / (TW / PX);
+    const int tiles_x = (a.wout + TW - 1) / TW;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int cob = blockIdx.y;                        // output-channel block
+    const int b = blockIdx.z;
+    const int ox0 = tile_x * TW, oy0 = tile_y * TH;
+    const int ix0 = ox0 * STRIDE - 1, iy0 = oy0 * STRIDE - 1;
+
+    for (int i = tid; i < CIN * 9 * COB; i += NT) {
+        const int col = i % COB, ct = i / COB;
+        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
+    }
+
+    float acc[PY][PX][COT];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int c = 0; c < COT; ++c) acc[j][p][c] = 0.f;
+
+    for (int chunk = 0; chunk < CIN / CK; ++chunk) {
+        const int ci0 = chunk * CK;
+        const float* base;
+        long long cstride;
+        if (ci0 < CA) { base = a.inA + (long long)b * a.strideA_b + (long long)ci0 * a.strideA_c; cstride = a.strideA_c; }
+        else { base = a.inB + (long long)b * a.strideB_b + (long long)(ci0 - CA) * a.strideB_c; cstride = a.strideB_c; }
+        __syncthreads();                               // previous chunk fully consumed (and sW visible)
+        for (int i = tid; i < CK * G::IH * G::IW; i += NT) {
+            const int col = i % G::IW, rc = i / G::IW;
+            const int row = rc % G::IH, c = rc / G::IH;
+            const int gy = iy0 + row, gx = ix0 + col;
+            float v = 0.f;
+            if (gy >= 0 && gy < a.hin && gx >= 0 && gx < a.win) v = __ldg(base + c * cstride + (long long)gy * a.win + gx);
+            sIn[(c * G::IH + row) * G::IP + col] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < CK; ++c) {
+            const float* wrow = sW + ((ci0 + c) * 9) * COB + cog * COT;
+            const float* irow = sIn + (c * G::IH) * G::IP;
+            if (STRIDE == 1) {
+#pragma unroll
+                for (int r = 0; r < PY + 2; ++r) {
+                    const float* ip = irow + (PY * ty + r) * G::IP + PX * tx;
+                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
+                    const float2 v1 = *reinterpret_cast<const float2*>(ip + 4);
+                    const float in[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int j = r - ky;
+                        if (j < 0 || j >= PY) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[p + kx], wv[co], acc[j][p][co]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2 * PY + 1; ++r) {
+                    const float* ip = irow + (2 * PY * ty + r) * G::IP + 2 * PX * tx;
+                    float in[2 * PX + 1];
+#pragma unroll
+                    for (int q = 0; q < 2 * PX + 1; ++q) in[q] = ip[q];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int jj = r - ky;
+                        if (jj < 0 || (jj & 1) || jj / 2 >= PY) continue;
+                        const int j = jj / 2;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[2 * p + kx], wv[co], acc[j][p][co]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ epilogue
+    const int co_base = cob * COB + cog * COT;          // first global output channel of this thread
+    const size_t plane = (size_t)a.hout * a.wout;
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+        const int oy = oy0 + PY * ty + j;
+        if (oy >= a.hout) continue;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const int ox = ox0 + PX * tx + p;
+            if (ox >= a.wout) continue;
+            const size_t pix = (size_t)oy * a.wout + ox;
+#pragma unroll
+            for (int c = 0; c < COT; ++c) {
+                const int co = co_base + c;
+                float v = acc[j][p][c];
+                if (EPI == EPI_RELU) {
+                    a.out0[((size_t)b * COUT + co) * plane + pix] = fmaxf(v, 0.f);
+                } else if (EPI == EPI_GATES) {
+                    constexpr int HC = COUT / 2;
+                    v = sigmoid_f(v + __ldg(a.bias + co));
+                    if (co < HC) {                      // reset gate -> r*h
+                        const size_t o = ((size_t)b * HC + co) * plane + pix;
+                        a.out0[o] = v * a.hstate[o];
+                    } else {                            // update gate
+                        a.out1[((size_t)b * HC + (co - HC)) * plane + pix] = v;
+                    }
+                } else if (EPI == EPI_CAND) {
+                    const size_t o = ((size_t)b * COUT + co) * plane + pix;
+                    const float cand = tanhf(v + __ldg(a.bias + co));
+                    const float u = a.ugate[o];
+                    a.out0[o] = u * a.hstate[o] + (1.f - u) * cand;
+                } else {
+                    v += __ldg(a.bias + co);
+                    a.out0[((size_t)b * COUT + co) * plane + pix] = v;
+                    const int grp = (a.stats_split && co >= COUT / 2) ? 1 : 0;
+                    atomicAdd(a.stats + ((size_t)b * 2 + grp) * 2, (double)v);
+                    atomicAdd(a.stats + ((size_t)b * 2 + grp) * 2 + 1, (double)v * (double)v);
+                }
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed persistent variant (the fast path; needs w % 4 == 0).
+//
+// A CTA owns one block of COB output channels (blockIdx.y), keeps that block's weights resident in
+// shared memory, and walks over output tiles (32 x TH pixels of one batch item) with stride gridDim.x.
+// The (tile, input-channel step) sequence is flattened into one stream that flows through a ring of
+// NSTAGE shared-memory slots: one elected thread keeps NSTAGE-1 steps of TMA boxes in flight (so the
+// boxes of the next tile land while the current tile is still computing and storing), every box
+// carries the 1-pixel halo with out-of-image elements zero-filled by the TMA unit (= the convolution's
+// zero padding), and one __syncthreads per step hands a consumed slot back to the producer.
+// A step is KSPLIT chunks of CKT input channels, consumed in parallel by KSPLIT thread groups whose
+// partial sums are reduced through shared memory (small output-channel counts and small planes get
+// their parallelism from there and from PY = 1 patches).
+// ------------------------------------------------------------------------------------------------
+template <int CA, int CB, int COUT, int COB, int STRIDE, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
+struct V2Cfg {
+    static constexpr int TW = 32;
+    static constexpr int CIN = CA + CB, NCHUNK = CIN / CKT, NSTEP = NCHUNK / KSPLIT, NCOG = COB / COT;
+    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
+    // the innermost TMA start coordinate must be 16-byte aligned (tools/tma_probe.cu), so the box
+    // starts 4 columns left of the tile; the 1-pixel halo column is tile column 3
+    static constexpr int IP = STRIDE == 1 ? TW + 8 : 2 * TW + 8;
+    static constexpr int GROUP = (TW / PX) * (TH / PY);
+    static constexpr int NT = GROUP * NCOG * KSPLIT;
+    static constexpr int CHUNK_FLOATS = CKT * IH * IP;
+    static constexpr int STEP_FLOATS = KSPLIT * CHUNK_FLOATS;
+    static constexpr int NACC = PY * PX * COT;
+    static constexpr int RED_FLOATS = (KSPLIT - 1) * GROUP * NCOG * NACC;
+    static constexpr int W_FLOATS = CIN * 9 * COB;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(NSTAGE * STEP_FLOATS + W_FLOATS + RED_FLOATS) + 8 * NSTAGE;
+    static_assert(NCHUNK % KSPLIT == 0, "KSPLIT must divide the chunk count");
+    static_assert(GROUP % 32 == 0, "warps must be uniform in (k-slice, channel group)");
+    static_assert(TH % PY == 0 && CA % CKT == 0 && CB % CKT == 0 && COB % COT == 0 && COUT % COB == 0, "bad blocking");
+    static_assert((CHUNK_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+};
+
+struct TileGrid { int tiles_x, tiles_y, ntiles; };          // ntiles = tiles_x * tiles_y * B
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
+__global__ void __launch_bounds__(V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>::NT)
+conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs a, TileGrid tg) {
+    using G = V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>;
+    constexpr int TW = G::TW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sIn = reinterpret_cast<float*>(smem_raw);                 // [NSTAGE][KSPLIT][CKT][IH][IP]
+    float* sW = sIn + NSTAGE * G::STEP_FLOATS;                       // [CIN][9][COB]
+    float* sRed = sW + G::W_FLOATS;                                  // [KSPLIT-1][NACC][GROUP*NCOG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + G::RED_FLOATS);
+
+    const int tid = threadIdx.x;
+    const int ks = tid / (G::GROUP * G::NCOG);
+    const int gt = tid - ks * (G::GROUP * G::NCOG);                  // thread index inside the k-slice
+    const int cog = gt / G::GROUP;
+    const int t = gt - cog * G::GROUP;
+    const int tx = t % (TW / PX), ty = t / (TW / PX);
+    const int cob = blockIdx.y;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int my_tiles = (tg.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * G::NSTEP;
+    const int tiles_per_item = tg.tiles_x * tg.tiles_y;
+
+    auto issue = [&](int g) {                                        // elected thread only
+        const int ti = g / G::NSTEP, step = g - ti * G::NSTEP;
+        const int tile = blockIdx.x + ti * gridDim.x;
+        const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
+        const int ox0 = (r % tg.tiles_x) * TW, oy0 = (r / tg.tiles_x) * TH;
+        const int slot = g % NSTAGE;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[slot], G::STEP_FLOATS * 4);
+#pragma unroll
+        for (int q = 0; q < KSPLIT; ++q) {
+            const int c = step * KSPLIT + q;
+            const bool fromA = c * CKT < CA;
+            const int plane = fromA ? b * a.planesA + c * CKT : b * a.planesB + (c * CKT - CA);
+            tma_load_4d(sIn + slot * G::STEP_FLOATS + q * G::CHUNK_FLOATS, fromA ? &tmA : &tmB, &bars[slot],
+                        ox0 * STRIDE - 4, oy0 * STRIDE - 1, fromA ? a.k : 0, plane);
+        }
+    };
+    if (tid == 0) {
+        for (int g = 0; g < NSTAGE - 1 && g < total; ++g) issue(g);
+    }
+    for (int i = tid; i < G::W_FLOATS; i += G::NT) {                 // resident weights, once per CTA
+        const int col = i % COB, ct = i / COB;
+        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
+    }
+    __syncthreads();
+
+    int g = 0;
+#pragma unroll 1
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        float acc[PY][PX][COT];
+#pragma unroll
+        for (int j = 0; j < PY; ++j)
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                for (int c = 0; c < COT; ++c) acc[j][p][c] = 0.f;
+
+#pragma unroll 1
+        for (int step = 0; step < G::NSTEP; ++step, ++g) {
+            if (tid == 0 && g + NSTAGE - 1 < total) issue(g + NSTAGE - 1);   // into the slot freed by step g-1
+            const int slot = g % NSTAGE;
+            mbar_wait(&bars[slot], (g / NSTAGE) & 1);
+            const int chunk = step * KSPLIT + ks;
+            const float* sC = sIn + slot * G::STEP_FLOATS + ks * G::CHUNK_FLOATS;
+#pragma unroll 2
+            for (int c = 0; c < CKT; ++c) {
+                const float* wrow = sW + ((chunk * CKT + c) * 9) * COB + cog * COT;
+                const float* irow = sC + (c * G::IH) * G::IP;
+                if (STRIDE == 1) {
+#pragma unroll
+                    for (int r = 0; r < PY + 2; ++r) {
+                        const float* ip = irow + (PY * ty + r) * G::IP + PX * tx;
+                        const float4 v0 = *reinterpret_cast<const float4*>(ip);
+                        const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
+                        const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
+                        const float in[6] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x};      // tile columns 4tx+3 .. 4tx+8
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int j = r - ky;
+                            if (j < 0 || j >= PY) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                                const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                    for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[p + kx], wv[co], acc[j][p][co]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2 * PY + 1; ++r) {
+                        const float* ip = irow + (2 * PY * ty + r) * G::IP + 2 * PX * tx;
+                        const float4 v0 = *reinterpret_cast<const float4*>(ip);
+                        const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
+                        const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
+                        const float in[9] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};   // columns 8tx+3 .. 8tx+11
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int jj = r - ky;
+                            if (jj < 0 || (jj & 1) || jj / 2 >= PY) continue;
+                            const int j = jj / 2;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
+                                const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
+                                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                                    for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[2 * p + kx], wv[co], acc[j][p][co]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                           // slot consumed: the producer may refill it
+        }
+
+        if (KSPLIT > 1) {                               // reduce the k-slices into slice 0
+            constexpr int GN = G::GROUP * G::NCOG;
+            if (ks > 0) {
+                float* dst = sRed + (size_t)(ks - 1) * G::NACC * GN + gt;
+#pragma unroll
+                for (int j = 0; j < PY; ++j)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+#pragma unroll
+                        for (int c = 0; c < COT; ++c) dst[((j * PX + p) * COT + c) * GN] = acc[j][p][c];
+            }
+            __syncthreads();
+            if (ks == 0) {
+#pragma unroll
+                for (int s = 0; s < KSPLIT - 1; ++s) {
+                    const float* src = sRed + (size_t)s * G::NACC * GN + gt;
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int p = 0; p < PX; ++p)
+#pragma unroll
+                            for (int c = 0; c < COT; ++c) acc[j][p][c] += src[((j * PX + p) * COT + c) * GN];
+                }
+            }
+            // sRed is rewritten only after the next tile's steps, each of which ends in a __syncthreads
+        }
+        if (ks != 0) continue;
+
+        // -------------------------------------------------------------- epilogue (float4 along x)
+        const int tile = blockIdx.x + ti * gridDim.x;
+        const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
+        const int ox0 = (rr % tg.tiles_x) * TW, oy0 = (rr / tg.tiles_x) * TH;
+        const int co_base = cob * COB + cog * COT;
+        const size_t plane = (size_t)a.hout * a.wout;
+        const int ox = ox0 + PX * tx;
+        float ssum = 0.f, ssq = 0.f;                    // RAW_STATS partials
+        if (ox < a.wout) {                              // wout % 4 == 0: a float4 is all in or all out
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                const int oy = oy0 + PY * ty + j;
+                if (oy >= a.hout) continue;
+                const size_t pix = (size_t)oy * a.wout + ox;
+#pragma unroll
+                for (int c = 0; c < COT; ++c) {
+                    const int co = co_base + c;
+                    float v[4] = {acc[j][0][c], acc[j][1][c], acc[j][2][c], acc[j][3][c]};
+                    if (EPI == EPI_RELU) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) v[p] = fmaxf(v[p], 0.f);
+                        *reinterpret_cast<float4*>(a.out0 + ((size_t)b * COUT + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else if (EPI == EPI_GATES) {
+                        constexpr int HC = COUT / 2;
+                        const float bc = __ldg(a.bias + co);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) v[p] = sigmoid_f(v[p] + bc);
+                        if (co < HC) {                  // reset gate -> r*h
+                            const size_t o = ((size_t)b * HC + co) * plane + pix;
+                            const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
+                            *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0] * hh.x, v[1] * hh.y, v[2] * hh.z, v[3] * hh.w);
+                        } else {
+                            *reinterpret_cast<float4*>(a.out1 + ((size_t)b * HC + (co - HC)) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    } else if (EPI == EPI_CAND) {
+                        const size_t o = ((size_t)b * COUT + co) * plane + pix;
+                        const float bc = __ldg(a.bias + co);
+                        const float4 u = *reinterpret_cast<const float4*>(a.ugate + o);
+                        const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
+                        const float uu[4] = {u.x, u.y, u.z, u.w}, hv[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanhf(v[p] + bc);
+                        *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+                        const float bc = __ldg(a.bias + co);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) { v[p] += bc; ssum += v[p]; ssq = fmaf(v[p], v[p], ssq); }
+                        *reinterpret_cast<float4*>(a.out0 + ((size_t)b * COUT + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_RAW_STATS) {                     // per-warp partial moments -> fp64 atomics (one pair per warp)
+            double ds = (double)ssum, dq = (double)ssq;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
+            if ((tid & 31) == 0) {
+                const int grp = (a.stats_split && co_base >= COUT / 2) ? 1 : 0;
+                atomicAdd(a.stats + ((size_t)b * 2 + grp) * 2, ds);
+                atomicAdd(a.stats + ((size_t)b * 2 + grp) * 2 + 1, dq);
+            }
+        }
+    }
+}
+
+// ---- per-layer plan: configuration + tensor maps, built once per regulariser call -----------------
+struct ConvPlan {
+    int cfg;                 // 0 BIG (32x16 tiles, 4x2 patches), 1 MID (32x8, 4x1), 2 SMALL (MID + split-K)
+    int ctas;                // persistent CTAs per output-channel block
+    TileGrid tg;
+    CUtensorMap tA, tB;
+    ConvArgs args;
+};
+
+inline int sm_count() {
+    static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    return n;
+}
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
+static cudaError_t launch_v2(ConvPlan& p, int B, cudaStream_t st) {
+    using G = V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>;
+    auto kern = conv3x3_v2_kernel<CA, CB, COUT, COB, STRIDE, EPI, TH, PY, KSPLIT, CKT, NSTAGE>;
+    static int per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 64 ? dev : 63;
+    if (per_sm[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::NT, G::SMEM);
+        if (e != cudaSuccess) return e;
+        per_sm[dev] = n > 0 ? n : 1;
+    }
+    p.tg.tiles_x = (p.args.wout + 31) / 32;
+    p.tg.tiles_y = (p.args.hout + TH - 1) / TH;
+    p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
+    const int ncob = COUT / COB;
+    int ctas = (sm_count() * per_sm[dev]) / ncob;
+    if (ctas < 1) ctas = 1;
+    if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
+    dim3 grid(ctas, ncob, 1);
+    kern<<<grid, G::NT, G::SMEM, st>>>(p.tA, p.tB, p.args, p.tg);
+    return cudaGetLastError();
+}
+
+// Ring depth: as many steps in flight as fit ~60 KB of shared memory per CTA (3-4 CTAs per SM), at least 2.
+template <int CIN, int COB, int STRIDE, int TH, int KSPLIT, int NSTEP>
+struct RingDepth {
+    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1, IP = STRIDE == 1 ? 40 : 72;
+    static constexpr int STEP_BYTES = KSPLIT * CK * IH * IP * 4;
+    static constexpr int budget = 60 * 1024 - CIN * 9 * COB * 4;
+    static constexpr int fit = budget / STEP_BYTES;
+    static constexpr int value = fit < 2 ? 2 : (fit > 4 ? 4 : fit);
+};
+
+template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
+struct ConvLayer {
+    static constexpr int CIN = CA + CB, NCHUNK = CIN / CK;
+    static constexpr int KS_BIG = (COB == 8 && NCHUNK % 2 == 0) ? 2 : 1;      // 8-channel layers: two k-slices -> 4 warps
+    static constexpr int KS_SMALL = (NCHUNK % 4 == 0 && CIN < 128) ? 4 : (NCHUNK % 2 == 0 ? 2 : 1);   // 128 inputs: 74 KB of weights
+
+    static int choose_cfg(int hout, int wout, int B) {
+        const long long want = 148LL * 768;                       // ~24 warps per SM
+        const long long px = (long long)hout * wout * B;
+        const long long t_big = px / 8 * (COUT / COT), t_mid = px / 4 * (COUT / COT);
+        if (t_big >= want && STRIDE == 1) return 0;           // stride-2 boxes are 4x larger: 32x8 tiles at most
+        if (t_mid >= want || NCHUNK == 1) return 1;
+        return 2;
+    }
+    static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
+        p.args = a;
+        p.cfg = choose_cfg(a.hout, a.wout, B);
+        const int TH = p.cfg == 0 ? 16 : 8;
+        const int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
+        const int IP = STRIDE == 1 ? 40 : 72;
+        if (!make_tmap_4d(&p.tA, a.inA, a.win, a.hin, depthA, (long long)B * a.planesA, IP, IH, CK)) return false;
+        if (CB > 0) { if (!make_tmap_4d(&p.tB, a.inB, a.win, a.hin, 1, (long long)B * a.planesB, IP, IH, CK)) return false; }
+        else p.tB = p.tA;
+        return true;
+    }
+    static cudaError_t launch(ConvPlan& p, int B, cudaStream_t st) {
+        switch (p.cfg) {
+            case 0: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 16, 2, KS_BIG, CK, RingDepth<CIN, COB, STRIDE, 16, KS_BIG, NCHUNK / KS_BIG>::value>(p, B, st);
+            case 1: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, 1, CK, RingDepth<CIN, COB, STRIDE, 8, 1, NCHUNK>::value>(p, B, st);
+            default: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, KS_SMALL, CK, RingDepth<CIN, COB, STRIDE, 8, KS_SMALL, NCHUNK / KS_SMALL>::value>(p, B, st);
+        }
+    }
+};
+
+}  // namespace adamvs

@@ -441,6 +441,27 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
     }
 }
 
+// Any width / alignment / view count: the global-gather path alone.
+template <int C, int VS, int MODE>
+__global__ void __launch_bounds__(kWvThreads)
+warp_volume_plain_kernel(WarpVolArgs a, int nk) {
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    const int kchunk = blockIdx.x % nk, tile = blockIdx.x / nk;
+    const int tiles_x = (a.w + kPX - 1) / kPX;
+    const int x = (tile % tiles_x) * kPX + lane, y = (tile / tiles_x) * kPY + row;
+    if (x < a.w && y < a.h) warp_volume_slow<C, VS, MODE>(a, blockIdx.y, x, y, kchunk * kKC);
+}
+
+template <int C, int VS, int MODE>
+static int launch_warp_volume_plain(const WarpVolArgs& a, int B, cudaStream_t st) {
+    const int nk = (a.D + kKC - 1) / kKC;
+    const long long tiles = (long long)((a.w + kPX - 1) / kPX) * ((a.h + kPY - 1) / kPY);
+    if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
+    dim3 grid((unsigned)(tiles * nk), B, 1);
+    warp_volume_plain_kernel<C, VS, MODE><<<grid, kWvThreads, 0, st>>>(a, nk);
+    ADAMVS_LAUNCH_RESULT();
+}
+
 template <int C, int VS, int MODE>
 static int launch_warp_volume_tma(const WarpVolArgs& a, int B, cudaStream_t st) {
     constexpr size_t smem = sizeof(float) * 2 * VS * kCK * kBox + 2 * sizeof(uint64_t) + VS * 4 * sizeof(int);
@@ -537,4 +558,31 @@ extern "C" int adamvs_fused_volume_f32(const float* feat, const float* relproj,
     }
 #undef ADAMVS_FV_C
 #undef ADAMVS_FV
+}
+
+extern "C" int adamvs_variance_volume_f32(const float* feat, const float* relproj,
+                                          int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                                          float* volume, int B, int V, int C, int D, int h, int w, void* stream) {
+    ADAMVS_CHECK_ARG(feat && relproj && volume && B > 0 && B <= 65535 && D >= 2 && h > 0 && w > 0);
+    if (int e = check_hyp(hyp_mode, hyp_src, hyp_ncol, half_range)) return e;
+    const HypSpec hs{hyp_mode, hyp_src, hyp_ncol, half_range};
+    cudaStream_t st = (cudaStream_t)stream;
+    const WarpVolArgs a{feat, relproj, hs, nullptr, ADAMVS_EPS_DENOMINATOR, volume, D, h, w};
+    if (tma_eligible(feat, w, h)) {
+        const int rc = dispatch_warp_volume_tma<MODE_VARIANCE>(a, B, V, C, st);
+        if (rc != -100) return rc;
+    }
+#define ADAMVS_VV(CC, VV) return launch_warp_volume_plain<CC, VV, MODE_VARIANCE>(a, B, st)
+#define ADAMVS_VV_C(VV) switch (C) { case 8: ADAMVS_VV(8, VV); case 16: ADAMVS_VV(16, VV); case 32: ADAMVS_VV(32, VV); default: return ADAMVS_EINVAL; }
+    switch (V - 1) {
+        case 1: ADAMVS_VV_C(1)
+        case 2: ADAMVS_VV_C(2)
+        case 3: ADAMVS_VV_C(3)
+        case 4: ADAMVS_VV_C(4)
+        case 5: ADAMVS_VV_C(5)
+        case 6: ADAMVS_VV_C(6)
+        default: return ADAMVS_EINVAL;
+    }
+#undef ADAMVS_VV_C
+#undef ADAMVS_VV
 }

@@ -20,405 +20,10 @@
 //   5 gates2 / 6 cand2 at half resolution                                32 -> 32 / 32 -> 16
 //   7 up1     y   = relu(convT3x3 s2 (h2) + b + h1)                      16 -> 8
 //   8 out     logit = convT3x3 s2 (y) + b  (stages 1-2) | conv3x3(y)+b (stage 3); online softmax update
-#include "common.cuh"
-#include "tma.cuh"
+#include "conv3x3.cuh"
+#include "regress_fused.cuh"
 
 namespace adamvs {
-
-constexpr int PX = 4;     // thread patch width  (pixels, along x)
-constexpr int PY = 2;     // thread patch height
-constexpr int COT = 8;    // output channels per thread
-constexpr int CK = 8;     // input channels staged per shared-memory chunk
-
-enum { EPI_RELU = 0, EPI_GATES = 1, EPI_CAND = 2 };
-
-struct ConvArgs {
-    const float* inA; long long strideA_c, strideA_b;   // first  CA input channels: base, channel stride, batch stride
-    const float* inB; long long strideB_c, strideB_b;   // next   CB input channels
-    const float* wpk;      // packed weights [CIN][9][COUT]
-    const float* bias;     // [COUT] or nullptr
-    float* out0;           // RELU: out [B,COUT,hout,wout] | GATES: rh [B,HC,h,w] | CAND: h (read-modify-write)
-    float* out1;           // GATES: u [B,HC,h,w]
-    const float* hstate;   // GATES / CAND: h [B,HC,h,w]
-    const float* ugate;    // CAND: u [B,HC,h,w]
-    int hin, win, hout, wout;
-    int planesA, planesB;  // channels per batch item of the tensors behind inA / inB (TMA plane coordinate)
-    int k;                 // depth-plane coordinate of inA (conv1 reads plane k of the cost volume)
-};
-
-template <int STRIDE, int TW, int TH>
-struct TileGeom {
-    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
-    static constexpr int IW = STRIDE == 1 ? TW + 2 : 2 * TW + 1;
-    static constexpr int IP = STRIDE == 1 ? TW + 4 : 2 * TW + 4;     // row pitch, multiple of 4 floats
-    static constexpr int GROUP = (TW / PX) * (TH / PY);              // threads per output-channel group
-};
-
-template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TW, int TH>
-__global__ void __launch_bounds__((TW / PX) * (TH / PY) * (COB / COT))
-conv3x3_kernel(ConvArgs a) {
-    using G = TileGeom<STRIDE, TW, TH>;
-    constexpr int CIN = CA + CB;
-    constexpr int NT = G::GROUP * (COB / COT);
-    static_assert(CA % CK == 0 && CB % CK == 0, "channel groups must be chunk aligned");
-    static_assert(COB % COT == 0 && COUT % COB == 0, "bad output channel blocking");
-    extern __shared__ __align__(16) float smem[];
-    float* sW = smem;                                  // [CIN][9][COB]
-    float* sIn = smem + CIN * 9 * COB;                 // [CK][IH][IP]
-
-    const int tid = threadIdx.x;
-    const int cog = tid / G::GROUP;                    // output-channel group inside the block
-    const int t = tid - cog * G::GROUP;
-    const int tx = t % (TW / PX), ty = t / (TW / PX);
-    const int tiles_x = (a.wout + TW - 1) / TW;
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    const int cob = blockIdx.y;                        // output-channel block
-    const int b = blockIdx.z;
-    const int ox0 = tile_x * TW, oy0 = tile_y * TH;
-    const int ix0 = ox0 * STRIDE - 1, iy0 = oy0 * STRIDE - 1;
-
-    for (int i = tid; i < CIN * 9 * COB; i += NT) {
-        const int col = i % COB, ct = i / COB;
-        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
-    }
-
-    float acc[PY][PX][COT];
-#pragma unroll
-    for (int j = 0; j < PY; ++j)
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-#pragma unroll
-            for (int c = 0; c < COT; ++c) acc[j][p][c] = 0.f;
-
-    for (int chunk = 0; chunk < CIN / CK; ++chunk) {
-        const int ci0 = chunk * CK;
-        const float* base;
-        long long cstride;
-        if (ci0 < CA) { base = a.inA + (long long)b * a.strideA_b + (long long)ci0 * a.strideA_c; cstride = a.strideA_c; }
-        else { base = a.inB + (long long)b * a.strideB_b + (long long)(ci0 - CA) * a.strideB_c; cstride = a.strideB_c; }
-        __syncthreads();                               // previous chunk fully consumed (and sW visible)
-        for (int i = tid; i < CK * G::IH * G::IW; i += NT) {
-            const int col = i % G::IW, rc = i / G::IW;
-            const int row = rc % G::IH, c = rc / G::IH;
-            const int gy = iy0 + row, gx = ix0 + col;
-            float v = 0.f;
-            if (gy >= 0 && gy < a.hin && gx >= 0 && gx < a.win) v = __ldg(base + c * cstride + (long long)gy * a.win + gx);
-            sIn[(c * G::IH + row) * G::IP + col] = v;
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int c = 0; c < CK; ++c) {
-            const float* wrow = sW + ((ci0 + c) * 9) * COB + cog * COT;
-            const float* irow = sIn + (c * G::IH) * G::IP;
-            if (STRIDE == 1) {
-#pragma unroll
-                for (int r = 0; r < PY + 2; ++r) {
-                    const float* ip = irow + (PY * ty + r) * G::IP + PX * tx;
-                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
-                    const float2 v1 = *reinterpret_cast<const float2*>(ip + 4);
-                    const float in[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int j = r - ky;
-                        if (j < 0 || j >= PY) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
-                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[p + kx], wv[co], acc[j][p][co]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 2 * PY + 1; ++r) {
-                    const float* ip = irow + (2 * PY * ty + r) * G::IP + 2 * PX * tx;
-                    float in[2 * PX + 1];
-#pragma unroll
-                    for (int q = 0; q < 2 * PX + 1; ++q) in[q] = ip[q];
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int jj = r - ky;
-                        if (jj < 0 || (jj & 1) || jj / 2 >= PY) continue;
-                        const int j = jj / 2;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
-                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[2 * p + kx], wv[co], acc[j][p][co]);
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    // ------------------------------------------------------------------ epilogue
-    const int co_base = cob * COB + cog * COT;          // first global output channel of this thread
-    const size_t plane = (size_t)a.hout * a.wout;
-#pragma unroll
-    for (int j = 0; j < PY; ++j) {
-        const int oy = oy0 + PY * ty + j;
-        if (oy >= a.hout) continue;
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            const int ox = ox0 + PX * tx + p;
-            if (ox >= a.wout) continue;
-            const size_t pix = (size_t)oy * a.wout + ox;
-#pragma unroll
-            for (int c = 0; c < COT; ++c) {
-                const int co = co_base + c;
-                float v = acc[j][p][c];
-                if (EPI == EPI_RELU) {
-                    a.out0[((size_t)b * COUT + co) * plane + pix] = fmaxf(v, 0.f);
-                } else if (EPI == EPI_GATES) {
-                    constexpr int HC = COUT / 2;
-                    v = sigmoid_f(v + __ldg(a.bias + co));
-                    if (co < HC) {                      // reset gate -> r*h
-                        const size_t o = ((size_t)b * HC + co) * plane + pix;
-                        a.out0[o] = v * a.hstate[o];
-                    } else {                            // update gate
-                        a.out1[((size_t)b * HC + (co - HC)) * plane + pix] = v;
-                    }
-                } else {
-                    const size_t o = ((size_t)b * COUT + co) * plane + pix;
-                    const float cand = tanhf(v + __ldg(a.bias + co));
-                    const float u = a.ugate[o];
-                    a.out0[o] = u * a.hstate[o] + (1.f - u) * cand;
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// TMA-fed variant (the fast path; needs w % 4 == 0).  The whole input tile of the block — all CIN
-// channels with the 1-pixel halo, zero-filled outside the image by the TMA unit — is requested up
-// front as CIN/8 boxes, each signalling its own mbarrier, so the FFMA loop on chunk c overlaps the
-// arrival of chunks c+1.. and no thread spends instructions on address arithmetic or bounds checks.
-// Small planes (stage 1, or B = 1) get more parallelism from PY = 1 patches and from splitting the
-// input-channel chunks over KSPLIT warps groups, reduced through shared memory.
-// ------------------------------------------------------------------------------------------------
-template <int CA, int CB, int COUT, int COB, int STRIDE, int TH, int PY, int KSPLIT>
-struct TmaCfg {
-    static constexpr int TW = 32;
-    static constexpr int CIN = CA + CB, NCHUNK = CIN / CK, NCOG = COB / COT;
-    static constexpr int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
-    // the innermost TMA start coordinate must be 16-byte aligned (tools/tma_probe.cu), so the box
-    // starts 4 columns left of the tile; the 1-pixel halo column is tile column 3
-    static constexpr int IP = STRIDE == 1 ? TW + 8 : 2 * TW + 8;
-    static constexpr int GROUP = (TW / PX) * (TH / PY);
-    static constexpr int NT = GROUP * NCOG * KSPLIT;
-    static constexpr int CHUNK_FLOATS = CK * IH * IP;
-    static constexpr int NACC = PY * PX * COT;
-    static constexpr int RED_FLOATS = (KSPLIT - 1) * GROUP * NCOG * NACC;
-    static constexpr int W_FLOATS = CIN * 9 * COB;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(NCHUNK * CHUNK_FLOATS + W_FLOATS + RED_FLOATS) + 8 * NCHUNK;
-    static_assert(NCHUNK % KSPLIT == 0, "KSPLIT must divide the chunk count");
-    static_assert((GROUP * NCOG) % 32 == 0, "warps must be uniform in (k-slice, channel group)");
-    static_assert(TH % PY == 0 && CA % CK == 0 && CB % CK == 0 && COB % COT == 0 && COUT % COB == 0, "bad blocking");
-};
-
-template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT>
-__global__ void __launch_bounds__(TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>::NT)
-conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
-    using G = TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>;
-    constexpr int TW = G::TW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sIn = reinterpret_cast<float*>(smem_raw);                 // [NCHUNK][CK][IH][IP]
-    float* sW = sIn + G::NCHUNK * G::CHUNK_FLOATS;                   // [CIN][9][COB]
-    float* sRed = sW + G::W_FLOATS;                                  // [KSPLIT-1][NACC][GROUP*NCOG]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + G::RED_FLOATS);
-
-    const int tid = threadIdx.x;
-    const int ks = tid / (G::GROUP * G::NCOG);
-    const int gt = tid - ks * (G::GROUP * G::NCOG);                  // thread index inside the k-slice
-    const int cog = gt / G::GROUP;
-    const int t = gt - cog * G::GROUP;
-    const int tx = t % (TW / PX), ty = t / (TW / PX);
-    const int tiles_x = (a.wout + TW - 1) / TW;
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    const int cob = blockIdx.y;
-    const int b = blockIdx.z;
-    const int ox0 = tile_x * TW, oy0 = tile_y * TH;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int c = 0; c < G::NCHUNK; ++c) mbar_init(&bars[c], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int c = 0; c < G::NCHUNK; ++c) {
-            mbar_expect_tx(&bars[c], G::CHUNK_FLOATS * 4);
-            const bool fromA = c * CK < CA;
-            const int plane = fromA ? b * a.planesA + c * CK : b * a.planesB + (c * CK - CA);
-            tma_load_4d(sIn + c * G::CHUNK_FLOATS, fromA ? &tmA : &tmB, &bars[c],
-                        ox0 * STRIDE - 4, oy0 * STRIDE - 1, fromA ? a.k : 0, plane);
-        }
-    }
-    for (int i = tid; i < G::W_FLOATS; i += G::NT) {
-        const int col = i % COB, ct = i / COB;
-        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
-    }
-    __syncthreads();
-
-    float acc[PY][PX][COT];
-#pragma unroll
-    for (int j = 0; j < PY; ++j)
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-#pragma unroll
-            for (int c = 0; c < COT; ++c) acc[j][p][c] = 0.f;
-
-#pragma unroll 1
-    for (int chunk = ks; chunk < G::NCHUNK; chunk += KSPLIT) {
-        mbar_wait(&bars[chunk], 0);
-        const float* sC = sIn + chunk * G::CHUNK_FLOATS;
-#pragma unroll 2
-        for (int c = 0; c < CK; ++c) {
-            const float* wrow = sW + ((chunk * CK + c) * 9) * COB + cog * COT;
-            const float* irow = sC + (c * G::IH) * G::IP;
-            if (STRIDE == 1) {
-#pragma unroll
-                for (int r = 0; r < PY + 2; ++r) {
-                    const float* ip = irow + (PY * ty + r) * G::IP + PX * tx;
-                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
-                    const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
-                    const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
-                    const float in[6] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x};      // tile columns 4tx+3 .. 4tx+8
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int j = r - ky;
-                        if (j < 0 || j >= PY) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
-                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[p + kx], wv[co], acc[j][p][co]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 2 * PY + 1; ++r) {
-                    const float* ip = irow + (2 * PY * ty + r) * G::IP + 2 * PX * tx;
-                    const float4 v0 = *reinterpret_cast<const float4*>(ip);
-                    const float4 v1 = *reinterpret_cast<const float4*>(ip + 4);
-                    const float4 v2 = *reinterpret_cast<const float4*>(ip + 8);
-                    const float in[9] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};   // columns 8tx+3 .. 8tx+11
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int jj = r - ky;
-                        if (jj < 0 || (jj & 1) || jj / 2 >= PY) continue;
-                        const int j = jj / 2;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + (ky * 3 + kx) * COB + 4);
-                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                                for (int co = 0; co < COT; ++co) acc[j][p][co] = fmaf(in[2 * p + kx], wv[co], acc[j][p][co]);
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    if (KSPLIT > 1) {                                   // reduce the k-slices into slice 0
-        constexpr int GN = G::GROUP * G::NCOG;
-        if (ks > 0) {
-            float* dst = sRed + (size_t)(ks - 1) * G::NACC * GN + gt;
-#pragma unroll
-            for (int j = 0; j < PY; ++j)
-#pragma unroll
-                for (int p = 0; p < PX; ++p)
-#pragma unroll
-                    for (int c = 0; c < COT; ++c) dst[((j * PX + p) * COT + c) * GN] = acc[j][p][c];
-        }
-        __syncthreads();
-        if (ks > 0) return;
-#pragma unroll
-        for (int s = 0; s < KSPLIT - 1; ++s) {
-            const float* src = sRed + (size_t)s * G::NACC * GN + gt;
-#pragma unroll
-            for (int j = 0; j < PY; ++j)
-#pragma unroll
-                for (int p = 0; p < PX; ++p)
-#pragma unroll
-                    for (int c = 0; c < COT; ++c) acc[j][p][c] += src[((j * PX + p) * COT + c) * GN];
-        }
-    }
-
-    // ------------------------------------------------------------------ epilogue (float4 along x)
-    const int co_base = cob * COB + cog * COT;
-    const size_t plane = (size_t)a.hout * a.wout;
-    const int ox = ox0 + PX * tx;
-    if (ox >= a.wout) return;                           // wout % 4 == 0: a float4 is all in or all out
-    if (EPI == EPI_GATES) {
-        // r*h needs h at the output pixel: it is input channel CA + (co % HC), already in the tile
-        constexpr int HC = COUT / 2;
-        if (co_base < HC) {
-#pragma unroll
-            for (int c = 0; c < G::NCHUNK; ++c) if (c * CK >= CA) mbar_wait(&bars[c], 0);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < PY; ++j) {
-        const int oy = oy0 + PY * ty + j;
-        if (oy >= a.hout) continue;
-        const size_t pix = (size_t)oy * a.wout + ox;
-#pragma unroll
-        for (int c = 0; c < COT; ++c) {
-            const int co = co_base + c;
-            float v[4] = {acc[j][0][c], acc[j][1][c], acc[j][2][c], acc[j][3][c]};
-            if (EPI == EPI_RELU) {
-#pragma unroll
-                for (int p = 0; p < 4; ++p) v[p] = fmaxf(v[p], 0.f);
-                *reinterpret_cast<float4*>(a.out0 + ((size_t)b * COUT + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
-            } else if (EPI == EPI_GATES) {
-                constexpr int HC = COUT / 2;
-                const float bc = __ldg(a.bias + co);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) v[p] = sigmoid_f(v[p] + bc);
-                if (co < HC) {
-                    const int ci = CA + co;
-                    const float4 hh = *reinterpret_cast<const float4*>(
-                        sIn + (ci / CK) * G::CHUNK_FLOATS + ((ci % CK) * G::IH + PY * ty + j + 1) * G::IP + PX * tx + 4);
-                    v[0] *= hh.x; v[1] *= hh.y; v[2] *= hh.z; v[3] *= hh.w;
-                    *reinterpret_cast<float4*>(a.out0 + ((size_t)b * HC + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-                    *reinterpret_cast<float4*>(a.out1 + ((size_t)b * HC + (co - HC)) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
-                }
-            } else {
-                const size_t o = ((size_t)b * COUT + co) * plane + pix;
-                const float bc = __ldg(a.bias + co);
-                const float4 u = *reinterpret_cast<const float4*>(a.ugate + o);
-                const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
-                const float uu[4] = {u.x, u.y, u.z, u.w}, hv[4] = {hh.x, hh.y, hh.z, hh.w};
-#pragma unroll
-                for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanhf(v[p] + bc);
-                *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // 7: y = relu(convT3x3 s2 p1 op1 (h2; 16->8) + b + h1).  One thread per half-resolution pixel: it owns
@@ -481,143 +86,7 @@ upconv_add_relu_kernel(const float* __restrict__ in, const float* __restrict__ w
 }
 
 // ------------------------------------------------------------------------------------------------
-// 8: logit + online regression.  State per output pixel: (m, s, ws) for the softmax convention
-// (running max logit, sum exp(l-m), sum d*exp(l-m)) or (emax, esum, dsum) for the reference's
-// un-shifted predict convention.  Plane 0 initialises, plane D-1 finalises into depth/conf.
-// ------------------------------------------------------------------------------------------------
-// The 72+1 output-layer scalars ([8,1,3,3] ConvTranspose2d and [1,8,3,3] Conv2d are both ci*9+tap)
-// are staged in shared memory by each block straight from the reference-layout tensors.
-struct OutWeights { const float* w; const float* b; };
-
-__device__ __forceinline__ void stage_out_weights(const OutWeights& ow, float* s) {
-    if (threadIdx.x < 72) s[threadIdx.x] = __ldg(ow.w + threadIdx.x);
-    if (threadIdx.x == 72) s[72] = __ldg(ow.b);
-    __syncthreads();
-}
-
-struct RegressState { float* s0; float* s1; float* s2; };
-
-__device__ __forceinline__ void regress_update(const RegressState& st, size_t o, float logit, float dval, int k, int D,
-                                               int prob_mode, float* depth, float* conf) {
-    float a0, a1, a2;
-    if (k == 0) { a0 = prob_mode == ADAMVS_PROB_SOFTMAX ? -INFINITY : 0.f; a1 = 0.f; a2 = 0.f; }
-    else { a0 = st.s0[o]; a1 = st.s1[o]; a2 = st.s2[o]; }
-    if (prob_mode == ADAMVS_PROB_SOFTMAX) {
-        const float m = fmaxf(a0, logit);
-        const float scale = expf(a0 - m);           // 0 when a0 = -inf
-        const float e = expf(logit - m);
-        a1 = a1 * scale + e;
-        a2 = a2 * scale + dval * e;
-        a0 = m;
-        if (k == D - 1) { depth[o] = a2 / a1; conf[o] = 1.f / a1; return; }
-    } else {
-        const float e = expf(logit);
-        a0 = (a0 < e) ? e : a0;                     // adamvs.py:518-519
-        a2 = dval * e + a2;                         // adamvs.py:524
-        a1 = a1 + e;                                // adamvs.py:527
-        if (k == D - 1) { const float den = a1 + 1e-10f; depth[o] = a2 / den; conf[o] = a0 / den; return; }
-    }
-    st.s0[o] = a0; st.s1[o] = a1; st.s2[o] = a2;
-}
-
-// stage 3: logit = conv3x3(y; 8->1) + b at the same resolution
-__global__ void __launch_bounds__(128)
-out_conv_regress_kernel(const float* __restrict__ y, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
-                        float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
-                        int k, int D, int h, int w) {
-    __shared__ float sw[73];
-    stage_out_weights(ow, sw);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yy = blockIdx.y;
-    const int b = blockIdx.z;
-    if (x >= w) return;
-    const size_t hw = (size_t)h * w;
-    float acc = sw[72];
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-        const float* p = y + ((size_t)b * 8 + ci) * hw;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int gy = yy + ky - 1;
-            if (gy < 0 || gy >= h) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int gx = x + kx - 1;
-                if (gx < 0 || gx >= w) continue;
-                acc = fmaf(__ldg(p + (size_t)gy * w + gx), sw[ci * 9 + ky * 3 + kx], acc);
-            }
-        }
-    }
-    const int pix = yy * w + x;
-    const size_t o = (size_t)b * hw + pix;
-    if (logits_out) logits_out[((size_t)b * D + k) * hw + pix] = acc;
-    const HypLine line = hyp_line(hs, b, pix, (int)hw, D);
-    regress_update(st, o, acc, hyp_at(line, k), k, D, prob_mode, depth, conf);
-}
-
-// stages 1-2: logit = convT3x3 s2 (y; 8->1) + b at twice the resolution; the hypothesis of an output
-// pixel is the align_corners=False bilinear upsample of the plane's hypotheses (module.py:622).
-__global__ void __launch_bounds__(128)
-out_upconv_regress_kernel(const float* __restrict__ y, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
-                          float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
-                          int k, int D, int h, int w) {
-    __shared__ float sw[73];
-    stage_out_weights(ow, sw);
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int iy = blockIdx.y;
-    const int b = blockIdx.z;
-    if (ix >= w) return;
-    const size_t hw = (size_t)h * w;
-    const bool hx = ix + 1 < w, hy = iy + 1 < h;
-    float l00 = sw[72], l01 = sw[72], l10 = sw[72], l11 = sw[72];
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-        const float* p = y + ((size_t)b * 8 + ci) * hw + (size_t)iy * w + ix;
-        const float v00 = __ldg(p);
-        const float v01 = hx ? __ldg(p + 1) : 0.f;
-        const float v10 = hy ? __ldg(p + w) : 0.f;
-        const float v11 = (hx && hy) ? __ldg(p + w + 1) : 0.f;
-        const float* wt = sw + ci * 9;
-        l00 += v00 * wt[4];
-        l01 += v01 * wt[3] + v00 * wt[5];
-        l10 += v10 * wt[1] + v00 * wt[7];
-        l11 += v11 * wt[0] + v10 * wt[2] + v01 * wt[6] + v00 * wt[8];
-    }
-    const int Ho = 2 * h, Wo = 2 * w;
-    const size_t ohw = (size_t)Ho * Wo;
-    const float lg[4] = {l00, l01, l10, l11};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int oy = 2 * iy + (q >> 1), ox = 2 * ix + (q & 1);
-        float dval;
-        if (hs.mode == ADAMVS_HYP_PLANES) {
-            dval = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
-        } else {
-            const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
-            const float d00 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i0, (int)hw, D), k);
-            const float d01 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i1, (int)hw, D), k);
-            const float d10 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i0, (int)hw, D), k);
-            const float d11 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i1, (int)hw, D), k);
-            dval = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
-        }
-        const size_t o = (size_t)b * ohw + (size_t)oy * Wo + ox;
-        if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)oy * Wo + ox] = lg[q];
-        regress_update(st, o, lg[q], dval, k, D, prob_mode, depth, conf);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// weight packing: reference layouts -> [ci][tap][co]
-// ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_kernel(const float* __restrict__ w, float* __restrict__ pk, int cout, int cin, int transposed) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cout * cin * 9) return;
-    const int co = i % cout, t = (i / cout) % 9, ci = i / (cout * 9);
-    pk[i] = transposed ? w[((size_t)ci * cout + co) * 9 + t] : w[((size_t)co * cin + ci) * 9 + t];
-}
-
-// ------------------------------------------------------------------------------------------------
-// host-side launch helpers
+// host-side launch helpers (non-TMA fallback: any even h, w; fixed 16x16 tiles)
 // ------------------------------------------------------------------------------------------------
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TW, int TH>
 static cudaError_t launch_conv(const ConvArgs& a, int B, cudaStream_t st) {
@@ -635,67 +104,10 @@ static cudaError_t launch_conv(const ConvArgs& a, int B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Fallback launcher (any even h, w): fixed 16x16 tiles.
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
 static cudaError_t launch_conv_auto(const ConvArgs& a, int B, cudaStream_t st) {
     return launch_conv<CA, CB, COUT, COB, STRIDE, EPI, 16, 16>(a, B, st);
 }
-
-// ---- TMA path: per-layer plan (configuration + tensor maps), built once per regulariser call -----
-struct ConvPlan {
-    int cfg;                 // 0 BIG (TH16,PY2), 1 MID (TH8,PY1), 2 SMALL (TH8,PY1, split-K over all chunks)
-    CUtensorMap tA, tB;
-    ConvArgs args;
-};
-
-template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT>
-static cudaError_t launch_tma(const ConvPlan& p, int B, cudaStream_t st) {
-    using G = TmaCfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT>;
-    auto kern = conv3x3_tma_kernel<CA, CB, COUT, COB, STRIDE, EPI, TH, PY, KSPLIT>;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
-    }
-    const int tiles = ((p.args.wout + 31) / 32) * ((p.args.hout + TH - 1) / TH);
-    dim3 grid(tiles, COUT / COB, B);
-    kern<<<grid, G::NT, G::SMEM, st>>>(p.tA, p.tB, p.args);
-    return cudaGetLastError();
-}
-
-template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
-struct ConvLayer {
-    static constexpr int NCHUNK = (CA + CB) / CK;
-    static int choose_cfg(int hout, int wout, int B) {
-        const long long want = 148LL * 768;                       // ~24 warps per SM
-        const long long px = (long long)hout * wout * B;
-        const long long t_big = px / 8 * (COUT / COT), t_mid = px / 4 * (COUT / COT);
-        if (t_big >= want) return 0;
-        if (t_mid >= want || NCHUNK == 1) return 1;
-        return 2;
-    }
-    static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
-        p.args = a;
-        p.cfg = choose_cfg(a.hout, a.wout, B);
-        const int TH = p.cfg == 0 ? 16 : 8;
-        const int IH = STRIDE == 1 ? TH + 2 : 2 * TH + 1;
-        const int IP = STRIDE == 1 ? 40 : 72;
-        if (!make_tmap_4d(&p.tA, a.inA, a.win, a.hin, depthA, (long long)B * a.planesA, IP, IH, CK)) return false;
-        if (CB > 0) { if (!make_tmap_4d(&p.tB, a.inB, a.win, a.hin, 1, (long long)B * a.planesB, IP, IH, CK)) return false; }
-        else p.tB = p.tA;
-        return true;
-    }
-    static cudaError_t launch(const ConvPlan& p, int B, cudaStream_t st) {
-        switch (p.cfg) {
-            case 0: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 16, 2, 1>(p, B, st);
-            case 1: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, 1>(p, B, st);
-            default: return launch_tma<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, NCHUNK>(p, B, st);
-        }
-    }
-};
 
 using Gates1 = ConvLayer<8, 8, 16, 16, 1, EPI_GATES>;
 using Cand1 = ConvLayer<8, 8, 8, 8, 1, EPI_CAND>;
@@ -768,7 +180,7 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
     // one-off per call: weights into [ci][tap][co]; states to zero (adamvs.py:175-176 / 448-449)
     auto pack = [&](const float* src, float* dst, int cout, int cin, int tr) {
         const int n = cout * cin * 9;
-        pack_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, cout, cin, tr);
+        pack_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, cout, cin, tr, 0);
     };
     pack(hwts->conv1_w, ws.pk_conv1, 8, C, 0);
     pack(hwts->gates1_w, ws.pk_gates1, 16, 16, 0);
@@ -841,7 +253,7 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
         {
             dim3 grid((w + 127) / 128, h, B);
             if (out_up) out_upconv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
-            else out_conv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+            else out_conv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, nullptr, 0, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
         }
         ADAMVS_TRY(cudaGetLastError());
     }

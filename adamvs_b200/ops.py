@@ -23,7 +23,8 @@ INTERVAL_LAST_COLUMN, INTERVAL_FROM_RANGE = 0, 1
 EXPORTS = (
     "adamvs_abi_version", "adamvs_cascade_prepare", "adamvs_pair_score_f32", "adamvs_resize_bilinear_f32",
     "adamvs_fused_volume_f32", "adamvs_regnet_red_workspace_floats", "adamvs_regnet_red_f32",
-    "adamvs_softmax_regress_f32",
+    "adamvs_softmax_regress_f32", "adamvs_variance_volume_f32", "adamvs_regnet_msred_workspace_floats",
+    "adamvs_regnet_msred_f32",
 )
 
 
@@ -31,6 +32,13 @@ class RegnetWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "conv1_w", "gates1_w", "gates1_b", "cand1_w", "cand1_b", "conv2_w", "gates2_w", "gates2_b",
         "cand2_w", "cand2_b", "up1_w", "up1_b", "out_w", "out_b")]
+
+
+class MsredWeights(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("conv1_w", "conv2_w", "conv3_w")] +
+                [(n, ctypes.c_void_p * 4) for n in ("gate_w", "gate_b", "rnorm_w", "rnorm_b", "unorm_w", "unorm_b",
+                                                     "out_w", "out_b", "onorm_w", "onorm_b")] +
+                [(n, ctypes.c_void_p) for n in ("up3_w", "up2_w", "up1_w", "prob_w", "prob_b")])
 
 
 _lib = None
@@ -57,8 +65,14 @@ def lib() -> ctypes.CDLL:
         L.adamvs_regnet_red_f32.argtypes = [vp, ctypes.POINTER(RegnetWeights), ci, vp, ci, vp, ci, ci, vp, cs,
                                             vp, vp, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_softmax_regress_f32.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_variance_volume_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_regnet_msred_workspace_floats.argtypes = [ci, ci, ci, ci, ci]
+        L.adamvs_regnet_msred_workspace_floats.restype = cs
+        L.adamvs_regnet_msred_f32.argtypes = [vp, ctypes.POINTER(MsredWeights), ci, vp, ci, vp, ci, vp, cs,
+                                              vp, vp, vp, ci, ci, ci, ci, ci, vp]
         for name in EXPORTS:
-            if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats"):
+            if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats",
+                            "adamvs_regnet_msred_workspace_floats"):
                 getattr(L, name).restype = ci
         if L.adamvs_abi_version() != 1:
             raise RuntimeError("libadamvs_b200.so ABI version mismatch; rebuild")
@@ -234,3 +248,48 @@ def softmax_regress(logits: torch.Tensor, hyp: Hyp, prob_mode: int, n_per_batch:
         _check(lib().adamvs_softmax_regress_f32(_p(logits), *hyp.args(), prob_mode, _p(depth), _p(conf),
                                                 N, n_per_batch, D, h, w, _stream()), "softmax_regress")
     return depth, conf
+
+
+# ---- MS-REDNet (config 5) ----------------------------------------------------------------------------
+
+def variance_volume(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, D: int, out: Optional[torch.Tensor] = None):
+    """feat [B,V,C,h,w] -> variance over the reference and the warped source views [B,C,D,h,w]."""
+    feat = _f32c(feat, "feat")
+    B, V, C, h, w = feat.shape
+    if out is None:
+        out = torch.empty((B, C, D, h, w), device=feat.device, dtype=torch.float32)
+    with _timed("variance_volume", 1):
+        _check(lib().adamvs_variance_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
+                                                B, V, C, D, h, w, _stream()), "variance_volume")
+    return out
+
+
+def regnet_msred(volume: torch.Tensor, weights: dict, hyp: Hyp, prob_mode: int,
+                 workspace: Optional[torch.Tensor] = None, want_logits: bool = False):
+    """volume [B,C,D,h,w] -> depth, conf [B,h,w] (+ logits [B,D,h,w] when asked).  `weights`: field name of
+    MsredWeights -> tensor, or list of 4 tensors (index 0..3 = conv_gru1..conv_gru4) for the per-level fields."""
+    volume = _f32c(volume, "volume")
+    B, C, D, h, w = volume.shape
+    need = int(lib().adamvs_regnet_msred_workspace_floats(B, C, D, h, w))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), device=volume.device, dtype=torch.float32)
+    depth = torch.empty((B, h, w), device=volume.device, dtype=torch.float32)
+    conf = torch.empty((B, h, w), device=volume.device, dtype=torch.float32)
+    logits = torch.empty((B, D, h, w), device=volume.device, dtype=torch.float32) if want_logits else None
+    keep = []
+    st = MsredWeights()
+    for name, _ in MsredWeights._fields_:
+        v = weights[name]
+        if isinstance(v, (list, tuple)):
+            ts = [_f32c(t, name) for t in v]
+            keep.extend(ts)
+            setattr(st, name, (ctypes.c_void_p * 4)(*[t.data_ptr() for t in ts]))
+        else:
+            t = _f32c(v, name)
+            keep.append(t)
+            setattr(st, name, t.data_ptr())
+    with _timed("regnet_msred", 11 + 25 * D):
+        _check(lib().adamvs_regnet_msred_f32(_p(volume), ctypes.byref(st), *hyp.args(), prob_mode,
+                                             _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
+                                             B, C, D, h, w, _stream()), "regnet_msred")
+    return (depth, conf, logits) if want_logits else (depth, conf)

@@ -210,3 +210,65 @@ def state_dict_shapes(ndepths0: int = 48) -> Dict[str, List[int]]:
         shapes[f"{q}.upconv2d.weight"] = [8, 1, 3, 3] if i < 2 else [1, 8, 3, 3]
         shapes[f"{q}.upconv2d.bias"] = [1]
     return shapes
+
+
+def msred_state_dict_shapes() -> Dict[str, List[int]]:
+    """key -> shape for CascadeREDNet / Infer_CascadeREDNet (219 tensors + BatchNorm counters;
+    reference models/msrednet.py:29-88, 134-148)."""
+    shapes: Dict[str, List[int]] = {}
+
+    def bn(prefix: str, c: int):
+        shapes[prefix + ".weight"] = [c]
+        shapes[prefix + ".bias"] = [c]
+        shapes[prefix + ".running_mean"] = [c]
+        shapes[prefix + ".running_var"] = [c]
+        shapes[prefix + ".num_batches_tracked"] = []
+
+    def cbr(prefix: str, cin: int, cout: int, k: int):
+        shapes[prefix + ".conv.weight"] = [cout, cin, k, k]
+        bn(prefix + ".bn", cout)
+
+    b = 8
+    cbr("feature.conv0.0", 3, b, 3); cbr("feature.conv0.1", b, b, 3)
+    cbr("feature.conv1.0", b, 2 * b, 5); cbr("feature.conv1.1", 2 * b, 2 * b, 3); cbr("feature.conv1.2", 2 * b, 2 * b, 3)
+    cbr("feature.conv2.0", 2 * b, 4 * b, 5); cbr("feature.conv2.1", 4 * b, 4 * b, 3); cbr("feature.conv2.2", 4 * b, 4 * b, 3)
+    shapes["feature.out1.weight"] = [4 * b, 4 * b, 1, 1]
+    for name, cin, cout in (("feature.deconv1", 4 * b, 2 * b), ("feature.deconv2", 2 * b, b)):
+        shapes[name + ".deconv.conv.weight"] = [cin, cout, 3, 3]
+        bn(name + ".deconv.bn", cout)
+        cbr(name + ".conv", 2 * cout, cout, 3)
+    shapes["feature.out2.weight"] = [2 * b, 2 * b, 1, 1]
+    shapes["feature.out3.weight"] = [b, b, 1, 1]
+    for i, c in enumerate((4 * b, 2 * b, b)):
+        p = f"cost_regularization.{i}"
+        for l, (x, hc) in enumerate(((c, 8), (16, 16), (32, 32), (64, 64)), start=1):
+            g = f"{p}.conv_gru{l}"
+            shapes[g + ".gate_conv.weight"] = [2 * hc, x + hc, 3, 3]
+            shapes[g + ".gate_conv.bias"] = [2 * hc]
+            for n in ("reset_gate_norm", "update_gate_norm"):
+                shapes[f"{g}.{n}.weight"] = [hc]
+                shapes[f"{g}.{n}.bias"] = [hc]
+            shapes[g + ".output_conv.weight"] = [hc, x + hc, 3, 3]
+            shapes[g + ".output_conv.bias"] = [hc]
+            shapes[g + ".output_norm.weight"] = [hc]
+            shapes[g + ".output_norm.bias"] = [hc]
+        shapes[p + ".conv1.conv.weight"] = [16, c, 3, 3]
+        shapes[p + ".conv2.conv.weight"] = [32, 16, 3, 3]
+        shapes[p + ".conv3.conv.weight"] = [64, 32, 3, 3]
+        shapes[p + ".upconv3.conv.weight"] = [64, 32, 3, 3]
+        shapes[p + ".upconv2.conv.weight"] = [32, 16, 3, 3]
+        shapes[p + ".upconv1.conv.weight"] = [16, 8, 3, 3]
+        shapes[p + ".upconv2d.weight"] = [8, 1, 3, 3]
+        shapes[p + ".upconv2d.bias"] = [1]
+    return shapes
+
+
+def calibrate_msred_state_dict(sd: Dict[str, torch.Tensor], feature_std: Dict[str, float], gain: float) -> Dict[str, torch.Tensor]:
+    """MS-REDNet counterpart of calibrate_state_dict: O(1) features, sharpened output layer."""
+    sd = {k: v.clone() for k, v in sd.items()}
+    for stage, key in (("stage1", "feature.out1.weight"), ("stage2", "feature.out2.weight"),
+                       ("stage3", "feature.out3.weight")):
+        sd[key] = sd[key] / float(feature_std[stage])
+    for i in range(3):
+        sd[f"cost_regularization.{i}.upconv2d.weight"] = sd[f"cost_regularization.{i}.upconv2d.weight"] * gain
+    return sd

@@ -121,6 +121,42 @@ int adamvs_softmax_regress_f32(const float* logits,
                                int prob_mode, float* depth, float* conf,
                                int N, int n_per_batch, int D, int h, int w, void* stream);
 
+/* ---- MS-REDNet (BASELINE config 5; reference models/msrednet.py) ------------------------------------ */
+
+/* K5 - variance cost volume over the reference view and the V-1 warped source views; replaces the per-plane
+ * loop of InferDepthNet.forward (msrednet.py:402-420) / the whole-volume form of DepthNet.forward (:214-231):
+ *   volume[b,c,k,y,x] = (ref^2 + sum_v warp_v^2)/V - ((ref + sum_v warp_v)/V)^2
+ * feat: [B,V,C,h,w]; relproj: [B,V-1,12]; volume: [B,C,D,h,w]. */
+int adamvs_variance_volume_f32(const float* feat, const float* relproj,
+                               int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                               float* volume, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* K6 - four-level GroupNorm conv-GRU recurrent regulariser on -volume with the regression folded in; replaces
+ * slice_RED_Regularization.forward / RED_Regularization.forward (msrednet.py:355-372 / 150-181), ConvGRUCell2
+ * (module.py:54-106) and the regression (msrednet.py:422-436 / 233-240).  Index l = 0..3 is conv_gru1..conv_gru4
+ * (8/16/32/64 hidden channels at h, h/2, h/4, h/8).  Weights in the reference's layouts:
+ *   conv{1,2,3}_w [16,C,3,3] [32,16,3,3] [64,32,3,3] (stride 2, no bias);
+ *   gate_w[l] [2HC, X+HC, 3,3] gate_b[l] [2HC]; out_w[l] [HC, X+HC, 3,3] out_b[l] [HC]  (X = C,16,32,64);
+ *   rnorm/unorm/onorm _w/_b [l] [HC] (GroupNorm(1,HC) affine);
+ *   up{3,2,1}_w [64,32,3,3] [32,16,3,3] [16,8,3,3] (ConvTranspose2d stride 2, no bias);
+ *   prob_w [8,1,3,3] prob_b [1] (ConvTranspose2d stride 1).
+ * volume: [B,C,D,h,w] (h, w multiples of 8); depth, conf: [B,h,w]; logits_out optional [B,D,h,w]. */
+typedef struct adamvs_msred_weights {
+    const float *conv1_w, *conv2_w, *conv3_w;
+    const float *gate_w[4], *gate_b[4], *rnorm_w[4], *rnorm_b[4], *unorm_w[4], *unorm_b[4];
+    const float *out_w[4], *out_b[4], *onorm_w[4], *onorm_b[4];
+    const float *up3_w, *up2_w, *up1_w;
+    const float *prob_w, *prob_b;
+} adamvs_msred_weights;
+
+size_t adamvs_regnet_msred_workspace_floats(int B, int C, int D, int h, int w);
+
+int adamvs_regnet_msred_f32(const float* volume, const adamvs_msred_weights* host_weights,
+                            int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                            int prob_mode, float* workspace, size_t workspace_floats,
+                            float* depth, float* conf, float* logits_out,
+                            int B, int C, int D, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,5 +101,74 @@ def main():
               "conf range s3:", float(ow["photometric_confidence"].min()), float(ow["photometric_confidence"].max()))
 
 
+MSRED_CASES = {
+    # name: (B, H, W, ndepths, num_depth, gain, weight_seed, input_seed, store_intermediates)
+    "msred_small_d8": (1, 64, 96, (8, 4, 2), 32, 4.0, 41, 9, True),
+    "msred_batch2_d6": (2, 64, 128, (6, 4, 2), 24, 4.0, 42, 10, False),
+}
+
+
+def main_msred():
+    """Same for MS-REDNet (BASELINE config 5): the reference's CascadeREDNet / Infer_CascadeREDNet."""
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ROOT)
+    from adamvs_b200 import synth
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import contextlib
+    import importlib
+    import io
+    import types
+    pkg = types.ModuleType("refmodels")                     # the reference's models/ has no __init__.py and our repo has
+    pkg.__path__ = [os.path.join(REF, "models")]            # a package of the same name: bind the directory explicitly
+    sys.modules["refmodels"] = pkg
+    ref = importlib.import_module("refmodels.msrednet")
+    assert ref.__file__.startswith(REF), ref.__file__
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.set_num_threads(os.cpu_count())
+    for name, (B, H, W, ndepths, num_depth, gain, wseed, iseed, store) in MSRED_CASES.items():
+        imgs, proj, dv2 = synth.make_sample(B, H, W, 5, seed=iseed)
+        interval = (synth.DEPTH_MAX - synth.DEPTH_MIN) / num_depth
+        dv3 = torch.cat([dv2, torch.full((B, 1), interval)], 1)
+        sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), wseed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            whole = ref.CascadeREDNet(ndepths=list(ndepths), depth_interals_ratio=[4.0, 2.0, 1.0]).eval()
+            stream = ref.Infer_CascadeREDNet(num_depth=num_depth, ndepths=list(ndepths), depth_interals_ratio=[4.0, 2.0, 1.0]).eval()
+        whole.load_state_dict(sd)
+        with torch.no_grad():
+            f = whole.feature(imgs[:, 0])
+        fstd = {k: float(f[k].std()) for k in ("stage1", "stage2", "stage3")}
+        sd = synth.calibrate_msred_state_dict(sd, fstd, gain)
+        whole.load_state_dict(sd)
+        stream.load_state_dict(sd)
+        blob = {"meta_B": B, "meta_H": H, "meta_W": W, "meta_ndepths": np.array(ndepths), "meta_num_depth": num_depth,
+                "meta_gain": gain, "meta_wseed": wseed, "meta_iseed": iseed,
+                "meta_fstd": np.array([fstd["stage1"], fstd["stage2"], fstd["stage3"]], dtype=np.float64)}
+        grabbed, hooks = {}, []
+        if store:
+            for i in range(3):
+                hooks.append(whole.cost_regularization[i].register_forward_hook(
+                    lambda m, a, o, i=i: grabbed.__setitem__(f"whole_s{i + 1}_variance", a[0].detach().clone())
+                    or grabbed.__setitem__(f"whole_s{i + 1}_logits", o.detach().clone())))
+        with torch.no_grad():
+            ow = whole(imgs, proj, dv3)
+            for h in hooks:
+                h.remove()
+            os_ = stream(imgs, proj, dv2)
+        for tag, out in (("whole", ow), ("stream", os_)):
+            for s in ("stage1", "stage2", "stage3"):
+                blob[f"{tag}_{s}_depth"] = out[s]["depth"].numpy()
+                blob[f"{tag}_{s}_conf"] = out[s]["photometric_confidence"].numpy()
+        for k, v in grabbed.items():
+            blob[k] = v.numpy()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "stream conf range s3:",
+              float(os_["photometric_confidence"].min()), float(os_["photometric_confidence"].max()),
+              "depth range s3:", float(os_["depth"].min()), float(os_["depth"].max()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--msred-only" not in sys.argv:
+        main()
+    main_msred()

@@ -27,6 +27,20 @@ def rebuild_case(g):
     return sd, imgs, proj, dv2, dv3, dict(B=B, H=H, W=W, ndepths=ndepths, num_depth=num_depth)
 
 
+def rebuild_msred_case(g):
+    """MS-REDNet counterpart of rebuild_case."""
+    B, H, W = int(g["meta_B"]), int(g["meta_H"]), int(g["meta_W"])
+    ndepths = tuple(int(x) for x in g["meta_ndepths"])
+    num_depth = int(g["meta_num_depth"])
+    imgs, proj, dv2 = synth.make_sample(B, H, W, 5, seed=int(g["meta_iseed"]))
+    interval = (synth.DEPTH_MAX - synth.DEPTH_MIN) / num_depth
+    dv3 = torch.cat([dv2, torch.full((B, 1), interval)], 1)
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), int(g["meta_wseed"]))
+    fstd = dict(zip(("stage1", "stage2", "stage3"), [float(x) for x in g["meta_fstd"]]))
+    sd = synth.calibrate_msred_state_dict(sd, fstd, float(g["meta_gain"]))
+    return sd, imgs, proj, dv2, dv3, dict(B=B, H=H, W=W, ndepths=ndepths, num_depth=num_depth)
+
+
 def make_case(B, H, W, ndepths, num_depth, gain, wseed, iseed, feature_fn):
     """Seeded calibrated case for sizes that have no golden file; feature_fn(sd, img)->dict gives
     the features used for calibration (oracle on CPU or product on GPU — both see the result)."""

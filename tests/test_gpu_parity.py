@@ -316,3 +316,106 @@ def test_cpu_tensors_are_refused():
     m = _model("whole", sd, meta["ndepths"])
     with pytest.raises(ops.AdamvsError):
         m(imgs, proj, dv3)
+
+
+# ------------------------------------------------------------------------------------------------
+# MS-REDNet (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------
+
+def _msred_model(cls, sd, ndepths, num_depth):
+    from models.msrednet import CascadeREDNet, Infer_CascadeREDNet
+    if cls == "whole":
+        m = CascadeREDNet(ndepths=list(ndepths), depth_interals_ratio=[4.0, 2.0, 1.0])
+    else:
+        m = Infer_CascadeREDNet(num_depth=num_depth, ndepths=list(ndepths), depth_interals_ratio=[4.0, 2.0, 1.0])
+    m.load_state_dict(sd)
+    return m.to(_dev()).eval()
+
+
+@pytest.mark.parametrize("C,D,h,w", [(32, 5, 16, 24), (16, 4, 32, 64), (8, 6, 40, 56)])
+def test_variance_volume_vs_oracle(C, D, h, w):
+    """K5 (staged and global-gather paths: w = 24/56 are not TMA-eligible... 24 % 4 == 0 is) against the oracle."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    from oracle import msrednet_oracle as MO
+    B, V = 2, 5
+    g = torch.Generator().manual_seed(C + D)
+    feat = torch.randn(B, V, C, h, w, generator=g)
+    proj = torch.stack([synth.make_cameras(h, w, V - 1)["stage3"], synth.make_cameras(h, w, V - 1, jitter_seed=4)["stage3"]])
+    dv = torch.tensor([[520.0, 680.0], [540.0, 660.0]])
+    relproj, half = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 192, [D, D, D], [4.0, 2.0, 1.0])
+    cur = 600 + 20 * torch.randn(B, h, w, generator=g)
+    interval = (float(dv[0, 1]) - float(dv[0, 0])) / 192
+    for mode in ("planes", "pixel"):
+        if mode == "planes":
+            hyp, hyps = ops.Hyp(ops.HYP_PLANES, dv.to(_dev())), O.depth_hypotheses(dv, D, 0.0, [B, h, w])
+        else:
+            hyp, hyps = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half[1:2]), O.depth_hypotheses(cur, D, 2.0 * interval, [B, h, w])
+        want = MO.variance_volume([feat[:, v] for v in range(V)], proj, hyps)
+        got = ops.variance_volume(feat.to(_dev()), relproj[0], hyp, D).cpu()
+        assert abs_err(got, want) < 2e-4 * float(want.abs().max()), mode
+
+
+@pytest.mark.parametrize("C,D,h,w,prob", [(32, 4, 16, 24, "exp"), (16, 3, 32, 64, "softmax"), (8, 3, 64, 96, "exp")])
+def test_regnet_msred_vs_oracle(C, D, h, w, prob):
+    """K6: logits, depth and confidence against the oracle's plane loop (TMA and generic-tile layer paths)."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    from oracle import msrednet_oracle as MO
+    B = 2
+    g = torch.Generator().manual_seed(h + D)
+    i = {32: 0, 16: 1, 8: 2}[C]
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 23)
+    p = f"cost_regularization.{i}"
+    sd[p + ".upconv2d.weight"] = sd[p + ".upconv2d.weight"] * 4
+    vol = torch.rand(B, C, D, h, w, generator=g) * 2.0
+    cur = 600 + 10 * torch.randn(B, h, w, generator=g)
+    half_range = torch.tensor([3.3], dtype=torch.float32)
+    hyps = O.depth_hypotheses(cur, D, float(half_range) / (D / 2), [B, h, w])
+    logits_want = MO.red_regulariser(sd, p, vol)
+    if prob == "softmax":
+        pr = F.softmax(logits_want, 1)
+        depth_want, conf_want, mode = (pr * hyps).sum(1), pr.max(1)[0], ops.PROB_SOFTMAX
+    else:
+        e = logits_want.exp()
+        den = e.sum(1) + 1e-10
+        depth_want, conf_want, mode = (e * hyps).sum(1) / den, e.max(1)[0] / den, ops.PROB_EXP_EPS
+    import models.msrednet as M
+    holder = M._REDRegularisationParams(C)
+    holder.load_state_dict({k[len(p) + 1:]: v for k, v in sd.items() if k.startswith(p + ".")})
+    holder = holder.to(_dev())
+    hyp = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half_range.to(_dev()))
+    depth, conf, logits = ops.regnet_msred(vol.to(_dev()), holder.kernel_weights(), hyp, mode, want_logits=True)
+    assert abs_err(logits.cpu(), logits_want) < 1e-4 * max(1.0, float(logits_want.abs().max()))
+    assert rel_err(depth.cpu(), depth_want) < DEPTH_RTOL
+    assert abs_err(conf.cpu(), conf_want) < PROB_ATOL
+
+
+@pytest.mark.parametrize("name", ["msred_small_d8", "msred_batch2_d6"])
+@pytest.mark.parametrize("cls", ["whole", "stream"])
+def test_msred_forward_matches_reference_golden(name, cls):
+    from tests.helpers import rebuild_msred_case
+    g = load_golden(name)
+    sd, imgs, proj, dv2, dv3, meta = rebuild_msred_case(g)
+    m = _msred_model(cls, sd, meta["ndepths"], meta["num_depth"])
+    out = m(imgs.to(_dev()), _to_dev(proj), (dv3 if cls == "whole" else dv2).to(_dev()))
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], g[f"{cls}_{s}_depth"], g[f"{cls}_{s}_conf"], f"{name}/{cls}/{s}")
+    assert out["depth"] is out["stage3"]["depth"]
+
+
+def test_msred_forward_full_size_vs_oracle():
+    """BASELINE config 5 shape at reduced depth counts (the CPU oracle needs ~1 s per plane at 768x384):
+    5-view 768x384, ndepths 8/4/2, Infer_CascadeREDNet."""
+    from adamvs_b200 import synth
+    from oracle import msrednet_oracle as MO
+    imgs, proj, dv2 = synth.make_sample(1, 384, 768, 5, seed=23)
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 37)
+    f = MO.feature_net(sd, imgs[:, 0])
+    sd = synth.calibrate_msred_state_dict(sd, {k: float(f[k].std()) for k in f}, 4.0)
+    want = MO.infer_cascade_rednet_forward(sd, imgs, proj, dv2, num_depth=32, ndepths=(8, 4, 2))
+    m = _msred_model("stream", sd, (8, 4, 2), 32)
+    out = m(imgs.to(_dev()), _to_dev(proj), dv2.to(_dev()))
+    assert tuple(out["stage1"]["depth"].shape) == (1, 96, 192) and tuple(out["depth"].shape) == (1, 384, 768)
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], want[s]["depth"], want[s]["photometric_confidence"], f"msred-full/{s}")
