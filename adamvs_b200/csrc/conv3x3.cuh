@@ -470,6 +470,7 @@ inline int sm_count() {
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
 static cudaError_t launch_v2(ConvPlan& p, int B, cudaStream_t st) {
     using G = V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>;
+    static_assert(G::SMEM <= 227 * 1024, "configuration exceeds the 227 KB of shared memory a CTA can have");
     auto kern = conv3x3_v2_kernel<CA, CB, COUT, COB, STRIDE, EPI, TH, PY, KSPLIT, CKT, NSTAGE>;
     static int per_sm[64] = {0};
     int dev = 0;
@@ -509,8 +510,9 @@ template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
 struct ConvLayer {
     static constexpr int CIN = CA + CB, NCHUNK = CIN / CK;
     static constexpr int KS_BIG = (COB == 8 && NCHUNK % 2 == 0) ? 2 : 1;      // 8-channel layers: two k-slices -> 4 warps
-    static constexpr int KS_SMALL = (NCHUNK % 4 == 0 && CIN < 128) ? 4 : (NCHUNK % 2 == 0 ? 2 : 1);   // 128 inputs: 74 KB of weights
-
+    // split-K factor of the small-plane configuration, bounded by shared memory: stride-2 boxes are 3x larger
+    // (no split), 128 input channels keep 74 KB of weights resident (split by 2 at most)
+    static constexpr int KS_SMALL = STRIDE == 2 ? 1 : ((NCHUNK % 4 == 0 && CIN < 128) ? 4 : (NCHUNK % 2 == 0 ? 2 : 1));
     static int choose_cfg(int hout, int wout, int B) {
         const long long want = 148LL * 768;                       // ~24 warps per SM
         const long long px = (long long)hout * wout * B;

@@ -196,9 +196,13 @@ __device__ __forceinline__ bool cell_taps(const Ray& r, float d, int h, int w, f
     const float X = __fadd_rn(__fmul_rn(r.qx, d), r.tx);
     const float Y = __fadd_rn(__fmul_rn(r.qy, d), r.ty);
     const float Z = __fadd_rn(__fmul_rn(r.qz, d), r.tz);
-    const float rz = __frcp_rn(Z);                     // one correctly rounded reciprocal instead of two divisions:
-    const float u = __fmul_rn(X, rz);                  // <= 1.5 ulp on u, v (6e-5 px at u ~ 700), below the reference's own
-    const float v = __fmul_rn(Y, rz);                  // normalise / un-normalise round trip
+    // Correctly rounded divisions like the reference's xy / z.  Its normalise -> grid_sample un-normalise round trip
+    // is an identity whose fp32 roundings move a sample by a few ulp of u (~1e-4 px at x ~ 700); so do the fp32
+    // torch.inverse behind the relative projection and the GEMM order of rot @ xyz (measured: DESIGN.md §5), so no
+    // independent implementation can track the reference's sample positions closer than that and none of it is
+    // imitated here.
+    const float u = __fdiv_rn(X, Z);
+    const float v = __fdiv_rn(Y, Z);
     const bool ok = (Z > 0.f) && (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);
     const float fu = floorf(ok ? u : 0.f), fv = floorf(ok ? v : 0.f);
     x0 = (int)fu; y0 = (int)fv;

@@ -89,6 +89,12 @@ def feature_net(sd: SD, img: torch.Tensor, prefix: str = "feature") -> Dict[str,
 # homography warp — models/module.py:527-568
 # ------------------------------------------------------------------------------------------------
 
+# Test knob: evaluate the relative projection in fp64 (rounded once to fp32) instead of the reference's fp32
+# torch.inverse + matmul.  Mathematically the same function; the outputs move by the reference's own fp32
+# arithmetic noise, which tests use to state how closely ANY independent implementation can agree with it.
+RELPROJ_FP64 = False
+
+
 def homography_warp(src_fea, src_proj, ref_proj, depth_values):
     """src_fea [B,C,h,w]; projections [B,4,4]; depth_values [B,D] or [B,D,h,w] -> [B,C,D,h,w].
     Same op order as the reference (relative projection by inverse+matmul, rotate the pixel grid,
@@ -97,7 +103,10 @@ def homography_warp(src_fea, src_proj, ref_proj, depth_values):
     B, C, h, w = src_fea.shape
     D = depth_values.shape[1]
     with torch.no_grad():
-        rel = torch.matmul(src_proj, torch.inverse(ref_proj))
+        if RELPROJ_FP64:
+            rel = torch.matmul(src_proj.double(), torch.linalg.inv(ref_proj.double())).to(src_proj.dtype)
+        else:
+            rel = torch.matmul(src_proj, torch.inverse(ref_proj))
         R, t = rel[:, :3, :3], rel[:, :3, 3:4]
         ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=src_fea.device),
                                 torch.arange(w, dtype=torch.float32, device=src_fea.device), indexing="ij")
