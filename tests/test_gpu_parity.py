@@ -455,3 +455,20 @@ def test_msred_forward_full_size_vs_oracle():
     assert tuple(out["stage1"]["depth"].shape) == (1, 96, 192) and tuple(out["depth"].shape) == (1, 384, 768)
     _compare_msred(out, want, noise, "msred-full")
     print("msred full-size: reference arithmetic noise (depth rel, prob abs) per stage:", noise)
+
+
+@pytest.mark.parametrize("cfg", ["0", "1", "2"])
+def test_conv_tile_configurations_forced(cfg):
+    """The persistent conv kernels pick one of three tile configurations from the plane size (32x16 tiles with 4x2
+    patches, 32x8 with 4x1, the latter with split-K).  The large one is only chosen for batched full-size planes,
+    which the CPU oracle cannot check in seconds, so each configuration is forced (ADAMVS_CONV_CFG) in a fresh
+    process and the K3 and K6 kernel tests are re-run under it."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ADAMVS_CONV_CFG=cfg)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_regnet_red_vs_oracle or test_regnet_msred_vs_oracle or test_forward_matches_reference_golden"],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
