@@ -34,8 +34,12 @@ H, W, V = 384, 768, 5
 NDEPTHS = (48, 32, 8)
 RATIOS = (4.0, 2.0, 1.0)
 NUM_DEPTH = 192
+MS_NDEPTHS = (128, 32, 8)          # BASELINE config 5: MS-REDNet, D = 128 planes at the first stage
+MS_NUM_DEPTH = 512
 METRIC = "depth maps/sec, 5-view 768x384"
 UNIT = "depth_maps/s"
+MS_WORKLOAD = ("configs[4]: MS-REDNet (Infer_CascadeREDNet) 5-view 768x384, ndepths 128/32/8, fp32, random-init weights; "
+               "reference views sharded over ranks")
 WORKLOAD = ("configs[1]: Ada-MVS 5-view (1 ref + 4 src) 768x384 cascade inference, fp32, random-init weights; "
             "reference views are independent and are sharded over ranks (configs[2])")
 
@@ -49,10 +53,10 @@ def _peaks():
         return 6650.0, 1590.0, "fallback"
 
 
-def costvolume_algorithmic_bytes(B, C, D, h, w, Vs=4):
-    """every feature map read once, hypothesis source and weights read once,
+def costvolume_algorithmic_bytes(B, C, D, h, w, Vs=4, view_weights=True):
+    """every feature map read once, hypothesis source and (Ada-MVS) view weights read once,
     the aggregated volume written once (fp32)."""
-    return 4 * B * ((1 + Vs) * C * h * w + h * w + Vs * h * w + C * D * h * w)
+    return 4 * B * ((1 + Vs) * C * h * w + h * w + (Vs * h * w if view_weights else 0) + C * D * h * w)
 
 
 def regnet_flops(B, C, D, h, w):
@@ -62,6 +66,17 @@ def regnet_flops(B, C, D, h, w):
     per_plane = 18 * (C * 8 * full + 16 * 16 * full + 16 * 8 * full + 8 * 16 * half + 32 * 32 * half
                       + 32 * 16 * half + 16 * 8 * half + 8 * 1 * full)
     return B * D * per_plane
+
+
+def msred_flops(B, C, D, h, w):
+    """Conv FLOPs of one MS-REDNet regulariser sweep (reference models/msrednet.py:355-372)."""
+    px = h * w
+    macs = (C * 16 * px / 4 + 16 * 32 * px / 16 + 32 * 64 * px / 64                      # conv1..3 (stride 2)
+            + (128 * 128 + 128 * 64) * px / 64 + 64 * 32 * px / 64                       # GRU4, upconv3
+            + (64 * 64 + 64 * 32) * px / 16 + 32 * 16 * px / 16                           # GRU3, upconv2
+            + (32 * 32 + 32 * 16) * px / 4 + 16 * 8 * px / 4                              # GRU2, upconv1
+            + ((C + 8) * 16 + (C + 8) * 8) * px + 8 * px)                                 # GRU1, output layer
+    return int(B * D * 18 * macs)
 
 
 class ClockSampler:
@@ -109,20 +124,28 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_maps_per_s(n_maps=3, warmup=1):
-    """The oracle's CPU port of Infer_AdaMVSNet.forward, all host threads, B=1 (reference's own batch size)."""
+def cpu_reference_maps_per_s(n_maps=3, warmup=1, model="adamvs"):
+    """The oracle's CPU port of the predict class' forward, all host threads, B=1 (reference's own batch size)."""
     import torch
     from adamvs_b200 import synth
-    from oracle import adamvs_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     imgs, proj, dv = synth.make_sample(1, H, W, V, seed=0)
-    sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
-    f = O.feature_net(sd, imgs[:, 0])
-    sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+    if model == "adamvs":
+        from oracle import adamvs_oracle as O
+        sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
+        f = O.feature_net(sd, imgs[:, 0])
+        sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+        run = lambda: O.infer_adamvs_forward(sd, imgs, proj, dv, num_depth=NUM_DEPTH, ndepths=NDEPTHS, ratios=RATIOS)
+    else:
+        from oracle import msrednet_oracle as MO
+        sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 0)
+        f = MO.feature_net(sd, imgs[:, 0])
+        sd = synth.calibrate_msred_state_dict(sd, {k: float(f[k].std()) for k in f}, 4.0)
+        run = lambda: MO.infer_cascade_rednet_forward(sd, imgs, proj, dv, num_depth=MS_NUM_DEPTH, ndepths=MS_NDEPTHS, ratios=RATIOS)
     times = []
     for i in range(warmup + n_maps):
         t0 = time.perf_counter()
-        O.infer_adamvs_forward(sd, imgs, proj, dv, num_depth=NUM_DEPTH, ndepths=NDEPTHS, ratios=RATIOS)
+        run()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -135,12 +158,15 @@ def run_reference(args):
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
     steps = min(steps, 10)                                   # bounded sample: one depth map per step
-    mps, cores, times = cpu_reference_maps_per_s(n_maps=steps, warmup=min(warm, 2))
+    mps, cores, times = cpu_reference_maps_per_s(n_maps=steps, warmup=min(warm, 2), model=args.model)
     line = {
         "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(warm, 2), "ms_per_step": 1e3 / mps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "class": "Infer_AdaMVSNet", "ndepths": list(NDEPTHS), "num_depth": NUM_DEPTH,
+        "config": {"workload": WORKLOAD if args.model == "adamvs" else MS_WORKLOAD,
+                   "class": "Infer_AdaMVSNet" if args.model == "adamvs" else "Infer_CascadeREDNet",
+                   "ndepths": list(NDEPTHS if args.model == "adamvs" else MS_NDEPTHS),
+                   "num_depth": NUM_DEPTH if args.model == "adamvs" else MS_NUM_DEPTH,
                    "views": V, "arm": "oracle torch-CPU port of the reference's PyTorch path, B=1 per step (the "
                                       "reference's own batch size), all host threads"},
         "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -160,6 +186,8 @@ def main():
                     help="reference views per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="adamvs", choices=["adamvs", "msrednet"],
+                    help="adamvs = the headline (configs[1]/[2]); msrednet = BASELINE config 5")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,13 +211,18 @@ def main():
     steps, warm, B = max(1, args.steps), max(min_warm, args.warmup), max(1, args.batch)
 
     # ---- model: seeded random-init weights, calibrated so that probabilities are not uniform
+    msred = args.model == "msrednet"
     with open(os.devnull, "w") as devnull:
         stdout, sys.stdout = sys.stdout, devnull
         try:
-            model = Infer_AdaMVSNet(num_depth=NUM_DEPTH, ndepths=list(NDEPTHS), depth_intervals_ratio=list(RATIOS))
+            if msred:
+                from models.msrednet import Infer_CascadeREDNet
+                model = Infer_CascadeREDNet(num_depth=MS_NUM_DEPTH, ndepths=list(MS_NDEPTHS), depth_interals_ratio=list(RATIOS))
+            else:
+                model = Infer_AdaMVSNet(num_depth=NUM_DEPTH, ndepths=list(NDEPTHS), depth_intervals_ratio=list(RATIOS))
         finally:
             sys.stdout = stdout
-    sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes() if msred else synth.state_dict_shapes(NDEPTHS[0]), 0)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     NSETS = 3                                                # distinct input batches, cycled (not L2-hot)
@@ -199,7 +232,8 @@ def main():
         host.append((imgs.pin_memory(), {k: v.pin_memory() for k, v in proj.items()}, dv.pin_memory()))
     with torch.no_grad():
         f = model.feature(host[0][0][:1, 0].to(dev))
-    sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+    fstd = {k: float(f[k].std()) for k in f}
+    sd = synth.calibrate_msred_state_dict(sd, fstd, 4.0) if msred else synth.calibrate_state_dict(sd, fstd, 60.0)
     model.load_state_dict(sd)
     resident = [(i.to(dev), {k: v.to(dev) for k, v in p.items()}, d.to(dev)) for i, p, d in host]
 
@@ -269,27 +303,28 @@ def main():
         ms = [a.elapsed_time(b) for a, b in evs]
         per_kernel[name] = {"launches": len(ms), "ms_mean": sum(ms) / len(ms), "ms_total": sum(ms)}
     step_ms = ms_total / steps
-    shapes = {"stage1": (32, 48, H // 4, W // 4), "stage2": (16, 32, H // 2, W // 2), "stage3": (8, 8, H, W)}
+    nd = MS_NDEPTHS if msred else NDEPTHS
+    shapes = {"stage1": (32, nd[0], H // 4, W // 4), "stage2": (16, nd[1], H // 2, W // 2), "stage3": (8, nd[2], H, W)}
     kernels = {}
     for name, st in per_kernel.items():
         entry = {"ms_per_step": st["ms_total"] / steps, "share_of_step": st["ms_total"] / steps / step_ms}
         stage = name.split("/")[-1]
-        if name.startswith("fused_volume/"):
+        if name.startswith("fused_volume/") or name.startswith("variance_volume/"):
             C, D, h, w = shapes[stage]
-            by = costvolume_algorithmic_bytes(B, C, D, h, w)
+            by = costvolume_algorithmic_bytes(B, C, D, h, w, view_weights=not msred)
             entry.update({"bound": "hbm", "algorithmic_bytes": by, "achieved_GBps": by / st["ms_mean"] * 1e-6,
                           "frac_of_hbm_peak": by / st["ms_mean"] * 1e-6 / hbm_peak})
-        elif name.startswith("regnet_red/"):
+        elif name.startswith("regnet_red/") or name.startswith("regnet_msred/"):
             C, D, h, w = shapes[stage]
-            fl = regnet_flops(B, C, D, h, w)
+            fl = msred_flops(B, C, D, h, w) if msred else regnet_flops(B, C, D, h, w)
             entry.update({"bound": "fp32 FFMA (fp32 parity forbids tf32/bf16 operands)", "flops": fl,
                           "achieved_TFLOPs": fl / st["ms_mean"] * 1e-9,
                           "frac_of_ffma_peak": fl / st["ms_mean"] * 1e-9 / ffma_peak,
                           "frac_of_bf16_tensor_peak": fl / st["ms_mean"] * 1e-9 / tensor_peak})
         kernels[name] = entry
     # headline roofline: the fused warp + cost-volume kernel with the largest launch (stage 2)
-    dom = max((k for k in kernels if k.startswith("fused_volume/")), key=lambda k: kernels[k]["algorithmic_bytes"])
-    roofline = {"kernel": "fused_volume_kernel (K2) " + dom.split("/")[-1], "bound": "hbm",
+    dom = max((k for k in kernels if k.startswith(("fused_volume/", "variance_volume/"))), key=lambda k: kernels[k]["algorithmic_bytes"])
+    roofline = {"kernel": ("warp_volume_tma_kernel (K5 variance) " if msred else "warp_volume_tma_kernel (K2 fused volume) ") + dom.split("/")[-1], "bound": "hbm",
                 "achieved": kernels[dom]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"]}
@@ -311,8 +346,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "class": "Infer_AdaMVSNet", "ndepths": list(NDEPTHS), "num_depth": NUM_DEPTH,
-                   "views": V, "batch_per_gpu_per_step": B,
+        "config": {"workload": MS_WORKLOAD if msred else WORKLOAD,
+                   "class": "Infer_CascadeREDNet" if msred else "Infer_AdaMVSNet", "ndepths": list(nd),
+                   "num_depth": MS_NUM_DEPTH if msred else NUM_DEPTH, "views": V, "batch_per_gpu_per_step": B,
                    "weights": "seeded random init, calibrated (SURVEY A.6)",
                    "l2": f"{NSETS} distinct input batches cycled; >1 GB of cost volume written/read per step (>> 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -323,10 +359,10 @@ def main():
         "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
-        mps, cores, times = cpu_reference_maps_per_s(n_maps=3, warmup=1)
+        mps, cores, times = cpu_reference_maps_per_s(n_maps=3, warmup=1, model=args.model)
         line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "3 depth maps (B=1, same 5-view 768x384 workload), median, after 1 warm-up; "
-                                          "oracle torch-CPU port of Infer_AdaMVSNet.forward"}
+                                          "oracle torch-CPU port of the predict class' forward"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -15,6 +15,7 @@ kern) python tools/prof_kernels.py --batch 8 > gpurun_out/${TAG}_kernels_b8.json
 kern1) python tools/prof_kernels.py --batch 1 > gpurun_out/${TAG}_kernels_b1.jsonl 2> gpurun_out/${TAG}_kernels_b1.err; cat gpurun_out/${TAG}_kernels_b1.jsonl;;
 feat) python tools/prof_featurenet.py --batch 8 > gpurun_out/${TAG}_featurenet.jsonl 2> gpurun_out/${TAG}_featurenet.err; cat gpurun_out/${TAG}_featurenet.jsonl;;
 bench) python bench.py --steps 10 --warmup 3 --batch 8 > gpurun_out/${TAG}_bench_b8.json 2> gpurun_out/${TAG}_bench_b8.err; python tools/show_bench.py gpurun_out/${TAG}_bench_b8.json;;
+benchms) python bench.py --model msrednet --steps 5 --warmup 3 --batch 4 > gpurun_out/${TAG}_bench_msred_b4.json 2> gpurun_out/${TAG}_bench_msred_b4.err; python tools/show_bench.py gpurun_out/${TAG}_bench_msred_b4.json; tail -3 gpurun_out/${TAG}_bench_msred_b4.err;;
 bench1) python bench.py --steps 10 --warmup 3 --batch 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_b1.json 2> gpurun_out/${TAG}_bench_b1.err; python tools/show_bench.py gpurun_out/${TAG}_bench_b1.json;;
 ncu_k2) ncu --set full --clock-control none --import-source on -k regex:'fused_volume_kernel|pair_score_kernel|warp_volume' -s 2 -c 10 -f -o gpurun_out/${TAG}_k2 \
     python tools/prof_kernels.py --batch 8 --only k1,k2 --iters 1 > gpurun_out/${TAG}_ncu_k2.log 2>&1; export_rep gpurun_out/${TAG}_k2;;
