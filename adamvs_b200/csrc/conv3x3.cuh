@@ -13,7 +13,7 @@ constexpr int PY = 2;     // thread patch height
 constexpr int COT = 8;    // output channels per thread
 constexpr int CK = 8;     // input channels staged per shared-memory chunk
 
-enum { EPI_RELU = 0, EPI_GATES = 1, EPI_CAND = 2, EPI_RAW_STATS = 3 };
+enum { EPI_RELU = 0, EPI_GATES = 1, EPI_CAND = 2, EPI_RAW_STATS = 3, EPI_BIAS = 4 };   // BIAS: + bias[co], optional ReLU
 
 struct ConvArgs {
     const float* inA; long long strideA_c, strideA_b;   // first  CA input channels: base, channel stride, batch stride
@@ -29,6 +29,7 @@ struct ConvArgs {
     int k;                 // depth-plane coordinate of inA (conv1 reads plane k of the cost volume)
     double* stats;         // RAW_STATS: [B][2][2] = per batch item, per channel half, {sum, sum of squares}
     int stats_split;       // RAW_STATS: 1 = two halves of COUT are separate groups (gate conv), 0 = one group
+    int relu;              // BIAS: apply ReLU after the bias
 };
 
 template <int STRIDE, int TW, int TH>
@@ -178,6 +179,9 @@ conv3x3_kernel(ConvArgs a) {
                     const float cand = tanhf(v + __ldg(a.bias + co));
                     const float u = a.ugate[o];
                     a.out0[o] = u * a.hstate[o] + (1.f - u) * cand;
+                } else if (EPI == EPI_BIAS) {
+                    v += __ldg(a.bias + co);
+                    a.out0[((size_t)b * COUT + co) * plane + pix] = a.relu ? fmaxf(v, 0.f) : v;
                 } else {
                     v += __ldg(a.bias + co);
                     a.out0[((size_t)b * COUT + co) * plane + pix] = v;
@@ -432,6 +436,11 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                         for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanhf(v[p] + bc);
                         *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else if (EPI == EPI_BIAS) {
+                        const float bc = __ldg(a.bias + co);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) { v[p] += bc; if (a.relu) v[p] = fmaxf(v[p], 0.f); }
+                        *reinterpret_cast<float4*>(a.out0 + ((size_t)b * COUT + co) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
                         const float bc = __ldg(a.bias + co);
 #pragma unroll

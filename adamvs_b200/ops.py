@@ -24,7 +24,7 @@ EXPORTS = (
     "adamvs_abi_version", "adamvs_cascade_prepare", "adamvs_pair_score_f32", "adamvs_resize_bilinear_f32",
     "adamvs_fused_volume_f32", "adamvs_regnet_red_workspace_floats", "adamvs_regnet_red_f32",
     "adamvs_softmax_regress_f32", "adamvs_variance_volume_f32", "adamvs_regnet_msred_workspace_floats",
-    "adamvs_regnet_msred_f32",
+    "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
 )
 
 
@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.adamvs_regnet_msred_workspace_floats.restype = cs
         L.adamvs_regnet_msred_f32.argtypes = [vp, ctypes.POINTER(MsredWeights), ci, vp, ci, vp, ci, vp, cs,
                                               vp, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_conv3x3_supported.argtypes = [ci, ci, ci, ci]
+        L.adamvs_conv3x3_f32.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, vp]
         for name in EXPORTS:
             if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats",
                             "adamvs_regnet_msred_workspace_floats"):
@@ -293,3 +295,30 @@ def regnet_msred(volume: torch.Tensor, weights: dict, hyp: Hyp, prob_mode: int,
                                              _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
                                              B, C, D, h, w, _stream()), "regnet_msred")
     return (depth, conf, logits) if want_logits else (depth, conf)
+
+
+# ---- 3x3 convolutions of FeatureNet0 / CostRegNet2D (SURVEY.md 8f-1) -----------------------------------
+
+def conv3x3_supported(ca: int, cb: int, cout: int, stride: int) -> bool:
+    return bool(lib().adamvs_conv3x3_supported(int(ca), int(cb), int(cout), int(stride)))
+
+
+def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """[COUT,CIN,3,3] -> [CIN,9,COUT] (the layout the kernels keep resident in shared memory)."""
+    return w.permute(1, 2, 3, 0).reshape(w.shape[1], 9, w.shape[0]).contiguous()
+
+
+def conv3x3(xa: torch.Tensor, xb: Optional[torch.Tensor], wpk: torch.Tensor, bias: torch.Tensor, relu: bool, stride: int = 1):
+    """act(conv3x3(cat(xa, xb)) + bias): xa [N,CA,h,w], xb [N,CB,h,w] or None, wpk from pack_conv3x3_weight."""
+    xa = _f32c(xa, "xa")
+    N, CA, h, w = xa.shape
+    CB = 0
+    if xb is not None:
+        xb = _f32c(xb, "xb")
+        CB = xb.shape[1]
+    COUT = wpk.shape[2]
+    out = torch.empty((N, COUT, h // stride, w // stride), device=xa.device, dtype=torch.float32)
+    with _timed("conv3x3", 1):
+        _check(lib().adamvs_conv3x3_f32(_p(xa), CA, _p(xb), CB, _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu),
+                                        int(stride), _p(out), N, COUT, h, w, _stream()), "conv3x3")
+    return out

@@ -157,6 +157,17 @@ int adamvs_regnet_msred_f32(const float* volume, const adamvs_msred_weights* hos
                             float* depth, float* conf, float* logits_out,
                             int B, int C, int D, int h, int w, void* stream);
 
+/* ---- 3x3 convolutions of the 2-D networks around the path --------------------------- */
+
+/* out = act(conv3x3(cat(inA, inB), w) + bias), padding 1, stride 1 or 2; replaces Conv2d/ConvBnReLU with eval-mode
+ * BatchNorm folded by the caller (module.py:164-199, 254-261) in FeatureNet0 (adamvs.py:57-104) and CostRegNet2D
+ * (adamvs.py:198-238), and DeConv2dFuse's cat + conv (module.py:519-523).
+ * inA [N,CA,hin,win], inB [N,CB,hin,win] or NULL (CB = 0); wpk: weights re-laid as [CA+CB][9][COUT]; bias [COUT];
+ * out [N,COUT,hin/stride,win/stride].  Channel combinations: adamvs_conv3x3_supported(). */
+int adamvs_conv3x3_supported(int CA, int CB, int COUT, int stride);
+int adamvs_conv3x3_f32(const float* inA, int CA, const float* inB, int CB, const float* wpk, const float* bias,
+                       int relu, int stride, float* out, int N, int COUT, int hin, int win, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

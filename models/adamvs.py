@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from adamvs_b200 import cascade as _cascade
+from adamvs_b200 import ops as _ops
 
 __all__ = ["AdaMVSNet", "Infer_AdaMVSNet", "cas_mvs_vis_loss", "FeatureNet0", "CostRegNet2D"]
 
@@ -36,11 +37,19 @@ class _ConvBN(nn.Module):
             self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
         self.bn = nn.BatchNorm2d(cout)
 
-    def forward(self, x):
-        if self.training or not _FOLD_BN:
-            return F.relu(self.bn(self.conv(x)), inplace=True)
-        w, b = _folded(self.conv, self.bn)
+    def forward(self, x, x2=None):
+        """x2: optional second tensor, concatenated behind x along the channels (read in place by the native conv)."""
         c = self.conv
+        if self.training or not _FOLD_BN:
+            if x2 is not None:
+                x = torch.cat((x, x2), 1)
+            return F.relu(self.bn(c(x)), inplace=True)
+        w, b, wpk = _folded(c, self.bn)
+        if wpk is not None and _NATIVE_CONV and x.is_cuda and x.dtype == torch.float32 and \
+                _ops.conv3x3_supported(x.shape[1], 0 if x2 is None else x2.shape[1], c.out_channels, c.stride[0]):
+            return _ops.conv3x3(x, x2, wpk, b, True, c.stride[0])
+        if x2 is not None:
+            x = torch.cat((x, x2), 1)
         if isinstance(c, nn.ConvTranspose2d):
             y = F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation)
         else:
@@ -49,23 +58,33 @@ class _ConvBN(nn.Module):
 
 
 _FOLD_BN = True      # eval-mode BatchNorm is an affine map: fold it into the preceding bias-free conv
+_NATIVE_CONV = True  # 3x3 convolutions of FeatureNet0 / CostRegNet2D on adamvs_b200's FFMA kernels instead of cuDNN
+
+
+def _is_plain_3x3(conv):
+    return (isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and conv.kernel_size == (3, 3)
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.stride[0] == conv.stride[1])
 
 
 def _folded(conv, bn):
-    """(weight, bias) of conv followed by eval-mode BatchNorm, cached on the conv module and rebuilt
-    whenever any of the five tensors involved is modified or moved."""
-    src = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    """(weight, bias, packed weight | None) of conv followed by eval-mode BatchNorm (bn may be None: plain conv with
+    bias), cached on the conv module and rebuilt whenever any of the tensors involved is modified or moved."""
+    src = (conv.weight,) + ((bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else (conv.bias,))
     key = tuple((t.data_ptr(), t._version) for t in src)
     cache = conv.__dict__.get("_adamvs_folded")
     if cache is None or cache[0] != key:
         with torch.no_grad():
-            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-            shape = (1, -1, 1, 1) if isinstance(conv, nn.ConvTranspose2d) else (-1, 1, 1, 1)
-            w = (conv.weight * scale.reshape(shape)).contiguous()
-            b = (bn.bias - bn.running_mean * scale).contiguous()
-        cache = (key, w, b)
+            if bn is not None:
+                scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                shape = (1, -1, 1, 1) if isinstance(conv, nn.ConvTranspose2d) else (-1, 1, 1, 1)
+                w = (conv.weight * scale.reshape(shape)).contiguous()
+                b = (bn.bias - bn.running_mean * scale).contiguous()
+            else:
+                w, b = conv.weight.detach().contiguous(), conv.bias.detach().contiguous()
+            wpk = _ops.pack_conv3x3_weight(w) if _is_plain_3x3(conv) else None
+        cache = (key, w, b, wpk)
         conv.__dict__["_adamvs_folded"] = cache
-    return cache[1], cache[2]
+    return cache[1], cache[2], cache[3]
 
 
 class _UpFuse(nn.Module):
@@ -78,7 +97,7 @@ class _UpFuse(nn.Module):
         self.conv = _ConvBN(2 * cout, cout, 3, 1, 1)
 
     def forward(self, skip, x):
-        return self.conv(torch.cat((self.deconv(x), skip), 1))
+        return self.conv(self.deconv(x), skip)
 
 
 def _context_branch(pool, cin, cout):
@@ -146,7 +165,7 @@ class CostRegNet2D(nn.Module):
         if self.training or not _FOLD_BN:
             return seq(x)
         c = seq[0]
-        w, b = _folded(c, seq[1])
+        w, b, _ = _folded(c, seq[1])
         return F.relu_(F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation))
 
     def forward(self, x):
@@ -157,6 +176,10 @@ class CostRegNet2D(nn.Module):
         y = e4 + self._up(self.conv7, y)
         y = e2 + self._up(self.conv9, y)
         y = e0 + self._up(self.conv11, y)
+        if not self.training and _NATIVE_CONV and y.is_cuda and y.dtype == torch.float32 and \
+                _ops.conv3x3_supported(y.shape[1], 0, self.prob.out_channels, 1):
+            w, b, wpk = _folded(self.prob, None)
+            return _ops.conv3x3(y, None, wpk, b, False, 1)
         return self.prob(y)
 
 

@@ -472,3 +472,24 @@ def test_conv_tile_configurations_forced(cfg):
                         "test_regnet_red_vs_oracle or test_regnet_msred_vs_oracle or test_forward_matches_reference_golden"],
                        cwd=root, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("ca,cb,cout,stride,relu,h,w", [
+    (8, 0, 8, 1, True, 40, 64), (16, 0, 16, 1, True, 36, 52), (32, 0, 32, 1, True, 24, 32), (16, 16, 16, 1, True, 32, 64),
+    (8, 8, 8, 1, True, 64, 96), (48, 0, 48, 1, False, 24, 48), (48, 0, 48, 2, True, 24, 48), (48, 0, 48, 1, True, 18, 30)])
+def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
+    """The 3x3 convolutions of FeatureNet0 / CostRegNet2D on the FFMA kernels (TMA and generic-tile paths) against
+    F.conv2d in fp32 on the CPU: same math, different summation order."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(ca + cout + h)
+    N = 3
+    xa = torch.randn(N, ca, h, w, generator=g)
+    xb = torch.randn(N, cb, h, w, generator=g) if cb else None
+    wt = torch.randn(cout, ca + cb, 3, 3, generator=g) / (3.0 * (ca + cb) ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    want = F.conv2d(xa if xb is None else torch.cat((xa, xb), 1), wt, bias, stride, 1)
+    want = F.relu(want) if relu else want
+    got = ops.conv3x3(xa.to(_dev()), None if xb is None else xb.to(_dev()), ops.pack_conv3x3_weight(wt).to(_dev()),
+                      bias.to(_dev()), relu, stride).cpu()
+    assert tuple(got.shape) == tuple(want.shape)
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))

@@ -1,8 +1,7 @@
 #!/usr/bin/env python
-"""Time FeatureNet0 and the stage-1 pair U-Net (the two cuDNN parts around the hot path) under a few
-cuDNN settings: BN folding on/off, cudnn.benchmark on/off, channels_last on/off, TF32 on/off.
-    python tools/prof_featurenet.py [--batch 8]"""
-import argparse, itertools, json, os, sys
+"""Time FeatureNet0 and the stage-1 pair U-Net (the 2-D networks around the hot path) with their 3x3 convolutions on
+adamvs_b200's FFMA kernels vs all-cuDNN fp32 (and cuDNN TF32 for reference).   python tools/prof_featurenet.py [--batch 8]"""
+import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -26,17 +25,9 @@ def time_it(fn, n=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-for fold, bench, cl, tf32 in itertools.product((True, False), (False, True), (False, True), (False, True)):
-    if tf32 and not (fold and bench): continue
-    M._FOLD_BN = fold
-    xx = x.contiguous(memory_format=torch.channels_last) if cl else x
-    ss = s.contiguous(memory_format=torch.channels_last) if cl else s
-    mm = m.to(memory_format=torch.channels_last) if cl else m.to(memory_format=torch.contiguous_format)
-    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=bench, deterministic=False, allow_tf32=tf32):
-        try:
-            tf = time_it(lambda: mm.feature(xx))
-            tp = time_it(lambda: mm.DepthNet[0].reg(ss))
-        except Exception as e:
-            print(json.dumps({"fold": fold, "benchmark": bench, "channels_last": cl, "tf32": tf32, "error": str(e)[:200]})); continue
-    print(json.dumps({"fold": fold, "benchmark": bench, "channels_last": cl, "tf32": tf32, "B": B,
-                      "featurenet_ms": tf, "pair_unet_ms": tp}), flush=True)
+for native, tf32 in ((True, False), (False, False), (False, True)):
+    M._NATIVE_CONV = native
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=tf32):
+        tf = time_it(lambda: m.feature(x))
+        tp = time_it(lambda: m.DepthNet[0].reg(s))
+    print(json.dumps({"native_3x3": native, "cudnn_tf32": tf32, "B": B, "featurenet_ms": tf, "pair_unet_ms": tp}), flush=True)
