@@ -38,7 +38,8 @@ using namespace adamvs;
 
 extern "C" int adamvs_conv3x3_supported(int CA, int CB, int COUT, int stride) {
     if (stride == 1) {
-        if (CB == 0) return (CA == 8 && COUT == 8) || (CA == 16 && COUT == 16) || (CA == 32 && COUT == 32) || (CA == 48 && COUT == 48);
+        if (CB == 0) return (CA == 8 && COUT == 8) || (CA == 16 && COUT == 16) || (CA == 32 && COUT == 32) || (CA == 48 && COUT == 48) ||
+                            (CA == 32 && COUT == 16) || (CA == 64 && COUT == 32);     // the 5x5 stride-2 convs in polyphase form
         return (CA == 16 && CB == 16 && COUT == 16) || (CA == 8 && CB == 8 && COUT == 8);
     }
     return stride == 2 && CB == 0 && CA == 48 && COUT == 48;
@@ -63,7 +64,83 @@ extern "C" int adamvs_conv3x3_f32(const float* inA, int CA, const float* inB, in
     switch (CA) {
         case 8: return run_conv<8, 0, 8, 1>(a, N, st);
         case 16: return run_conv<16, 0, 16, 1>(a, N, st);
-        case 32: return run_conv<32, 0, 32, 1>(a, N, st);
+        case 32: return COUT == 32 ? run_conv<32, 0, 32, 1>(a, N, st) : run_conv<32, 0, 16, 1>(a, N, st);
+        case 64: return run_conv<64, 0, 32, 1>(a, N, st);
         default: return run_conv<48, 0, 48, 1>(a, N, st);
     }
+}
+
+// ---- y = act(convT3x3 s2 p1 op1 (x; CIN -> COUT) + bias): Deconv2d + folded BatchNorm + ReLU (module.py:202-245) and
+// CostRegNet2D's up blocks (adamvs.py:212-225).  One thread per input pixel and block of 8 output channels; it owns the
+// 2x2 outputs that (iy,ix) is the top-left contributor of (tap table in regnet.cu).  wpk is [ci][tap][COUT].
+namespace adamvs {
+template <int CIN, int COUT>
+static __global__ void __launch_bounds__(128)
+deconv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ bias, int relu,
+                 float* __restrict__ out, int hin, int win) {
+    constexpr int COB = 8;
+    __shared__ float sW[CIN * 9 * COB];
+    const int cob = blockIdx.y % (COUT / COB), iy = blockIdx.y / (COUT / COB);
+    for (int i = threadIdx.x; i < CIN * 9 * COB; i += blockDim.x) sW[i] = __ldg(wpk + (size_t)(i / COB) * COUT + cob * COB + (i % COB));
+    __syncthreads();
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.z;
+    if (ix >= win) return;
+    const size_t ip = (size_t)hin * win;
+    const int wout = 2 * win;
+    const bool hx = ix + 1 < win, hy = iy + 1 < hin;
+    float acc[4][COB];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < COB; ++c) acc[q][c] = 0.f;
+    const float* pin = in + (size_t)b * CIN * ip + (size_t)iy * win + ix;
+#pragma unroll 4
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* p = pin + (size_t)ci * ip;
+        const float v00 = __ldg(p);
+        const float v01 = hx ? __ldg(p + 1) : 0.f;
+        const float v10 = hy ? __ldg(p + win) : 0.f;
+        const float v11 = (hx && hy) ? __ldg(p + win + 1) : 0.f;
+        const float* w = sW + ci * 9 * COB;
+#pragma unroll
+        for (int c = 0; c < COB; ++c) {
+            acc[0][c] = fmaf(v00, w[4 * COB + c], acc[0][c]);
+            acc[1][c] = fmaf(v01, w[3 * COB + c], fmaf(v00, w[5 * COB + c], acc[1][c]));
+            acc[2][c] = fmaf(v10, w[1 * COB + c], fmaf(v00, w[7 * COB + c], acc[2][c]));
+            acc[3][c] = fmaf(v11, w[0 * COB + c], fmaf(v10, w[2 * COB + c], fmaf(v01, w[6 * COB + c], fmaf(v00, w[8 * COB + c], acc[3][c]))));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COB; ++c) {
+        const float bc = __ldg(bias + cob * COB + c);
+        float r[4] = {acc[0][c] + bc, acc[1][c] + bc, acc[2][c] + bc, acc[3][c] + bc};
+        if (relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+        const size_t o = ((size_t)b * COUT + cob * COB + c) * 4 * ip + (size_t)(2 * iy) * wout + 2 * ix;
+        *reinterpret_cast<float2*>(out + o) = make_float2(r[0], r[1]);
+        *reinterpret_cast<float2*>(out + o + wout) = make_float2(r[2], r[3]);
+    }
+}
+
+template <int CIN, int COUT>
+static int launch_deconv(const float* in, const float* wpk, const float* bias, int relu, float* out, int N, int hin, int win, cudaStream_t st) {
+    if ((long long)hin * (COUT / 8) > 65535 || N > 65535) return ADAMVS_EINVAL;
+    dim3 grid((win + 127) / 128, hin * (COUT / 8), N);
+    deconv3x3_kernel<CIN, COUT><<<grid, 128, 0, st>>>(in, wpk, bias, relu, out, hin, win);
+    ADAMVS_LAUNCH_RESULT();
+}
+}  // namespace adamvs
+
+extern "C" int adamvs_deconv3x3_supported(int CIN, int COUT) {
+    return (CIN == 32 && COUT == 16) || (CIN == 16 && COUT == 8) || (CIN == 48 && COUT == 48);
+}
+
+extern "C" int adamvs_deconv3x3_f32(const float* in, const float* wpk, const float* bias, int relu, float* out,
+                                    int N, int CIN, int COUT, int hin, int win, void* stream) {
+    ADAMVS_CHECK_ARG(in && wpk && bias && out && N > 0 && hin > 0 && win > 0 && adamvs_deconv3x3_supported(CIN, COUT));
+    ADAMVS_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 8 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (CIN == 32) return launch_deconv<32, 16>(in, wpk, bias, relu, out, N, hin, win, st);
+    if (CIN == 16) return launch_deconv<16, 8>(in, wpk, bias, relu, out, N, hin, win, st);
+    return launch_deconv<48, 48>(in, wpk, bias, relu, out, N, hin, win, st);
 }

@@ -25,6 +25,7 @@ EXPORTS = (
     "adamvs_fused_volume_f32", "adamvs_regnet_red_workspace_floats", "adamvs_regnet_red_f32",
     "adamvs_softmax_regress_f32", "adamvs_variance_volume_f32", "adamvs_regnet_msred_workspace_floats",
     "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
+    "adamvs_deconv3x3_supported", "adamvs_deconv3x3_f32",
 )
 
 
@@ -70,6 +71,8 @@ def lib() -> ctypes.CDLL:
         L.adamvs_regnet_msred_workspace_floats.restype = cs
         L.adamvs_regnet_msred_f32.argtypes = [vp, ctypes.POINTER(MsredWeights), ci, vp, ci, vp, ci, vp, cs,
                                               vp, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_deconv3x3_supported.argtypes = [ci, ci]
+        L.adamvs_deconv3x3_f32.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv3x3_supported.argtypes = [ci, ci, ci, ci]
         L.adamvs_conv3x3_f32.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, vp]
         for name in EXPORTS:
@@ -322,3 +325,44 @@ def conv3x3(xa: torch.Tensor, xb: Optional[torch.Tensor], wpk: torch.Tensor, bia
         _check(lib().adamvs_conv3x3_f32(_p(xa), CA, _p(xb), CB, _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu),
                                         int(stride), _p(out), N, COUT, h, w, _stream()), "conv3x3")
     return out
+
+
+def deconv3x3_supported(cin: int, cout: int) -> bool:
+    return bool(lib().adamvs_deconv3x3_supported(int(cin), int(cout)))
+
+
+def pack_deconv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d weight [CIN,COUT,3,3] -> [CIN,9,COUT]."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).contiguous()
+
+
+def deconv3x3(x: torch.Tensor, wpk: torch.Tensor, bias: torch.Tensor, relu: bool):
+    """act(ConvTranspose2d(k=3, s=2, p=1, output_padding=1)(x) + bias): x [N,CIN,h,w] -> [N,COUT,2h,2w]."""
+    x = _f32c(x, "x")
+    N, CIN, h, w = x.shape
+    COUT = wpk.shape[2]
+    out = torch.empty((N, COUT, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    with _timed("deconv3x3", 1):
+        _check(lib().adamvs_deconv3x3_f32(_p(x), _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu), _p(out),
+                                          N, CIN, COUT, h, w, _stream()), "deconv3x3")
+    return out
+
+
+def polyphase_5x5_s2_weight(w: torch.Tensor) -> torch.Tensor:
+    """A 5x5 stride-2 padding-2 convolution equals a 3x3 stride-1 padding-1 convolution over the pixel-unshuffled
+    input (channel order c*4 + py*2 + px, as F.pixel_unshuffle): tap ky = 2*dy + 2 + py of the original kernel sits
+    at offset dy of phase py (and likewise in x); the 11 of 36 positions without a counterpart are zero.
+    w [COUT,CIN,5,5] -> [COUT,4*CIN,3,3]."""
+    cout, cin = w.shape[:2]
+    out = w.new_zeros(cout, cin, 2, 2, 3, 3)
+    for py in range(2):
+        for dy in range(-1, 2):
+            ky = 2 * dy + 2 + py
+            if not 0 <= ky < 5:
+                continue
+            for px in range(2):
+                for dx in range(-1, 2):
+                    kx = 2 * dx + 2 + px
+                    if 0 <= kx < 5:
+                        out[:, :, py, px, dy + 1, dx + 1] = w[:, :, ky, kx]
+    return out.reshape(cout, cin * 4, 3, 3)

@@ -168,6 +168,13 @@ int adamvs_conv3x3_supported(int CA, int CB, int COUT, int stride);
 int adamvs_conv3x3_f32(const float* inA, int CA, const float* inB, int CB, const float* wpk, const float* bias,
                        int relu, int stride, float* out, int N, int COUT, int hin, int win, void* stream);
 
+/* out = act(convT3x3 stride 2, padding 1, output_padding 1 (in; CIN -> COUT) + bias); replaces Deconv2d + BatchNorm (eval,
+ * folded by the caller) + ReLU (module.py:202-245) and CostRegNet2D's transposed blocks (adamvs.py:212-225).
+ * in [N,CIN,hin,win]; wpk: ConvTranspose2d weight [CIN,COUT,3,3] re-laid as [CIN][9][COUT]; out [N,COUT,2hin,2win]. */
+int adamvs_deconv3x3_supported(int CIN, int COUT);
+int adamvs_deconv3x3_f32(const float* in, const float* wpk, const float* bias, int relu, float* out,
+                         int N, int CIN, int COUT, int hin, int win, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,10 +44,11 @@ class _ConvBN(nn.Module):
             if x2 is not None:
                 x = torch.cat((x, x2), 1)
             return F.relu(self.bn(c(x)), inplace=True)
-        w, b, wpk = _folded(c, self.bn)
-        if wpk is not None and _NATIVE_CONV and x.is_cuda and x.dtype == torch.float32 and \
-                _ops.conv3x3_supported(x.shape[1], 0 if x2 is None else x2.shape[1], c.out_channels, c.stride[0]):
-            return _ops.conv3x3(x, x2, wpk, b, True, c.stride[0])
+        w, b, wpk, mode = _folded(c, self.bn)
+        if mode is not None and _NATIVE_CONV and x.is_cuda and x.dtype == torch.float32:
+            y = _native_conv(x, x2, wpk, b, mode, c, True)
+            if y is not None:
+                return y
         if x2 is not None:
             x = torch.cat((x, x2), 1)
         if isinstance(c, nn.ConvTranspose2d):
@@ -58,17 +59,45 @@ class _ConvBN(nn.Module):
 
 
 _FOLD_BN = True      # eval-mode BatchNorm is an affine map: fold it into the preceding bias-free conv
-_NATIVE_CONV = True  # 3x3 convolutions of FeatureNet0 / CostRegNet2D on adamvs_b200's FFMA kernels instead of cuDNN
+_NATIVE_CONV = True  # convolutions of FeatureNet0 / CostRegNet2D on adamvs_b200's kernels instead of cuDNN where supported
 
 
-def _is_plain_3x3(conv):
-    return (isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and conv.kernel_size == (3, 3)
-            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.stride[0] == conv.stride[1])
+def _conv_mode(conv):
+    """Which native kernel can run this conv: '3x3' (stride 1/2), 'poly' (5x5 stride 2 in polyphase form), 'deconv'
+    (3x3 stride-2 transposed), or None."""
+    if conv.groups != 1 or conv.dilation != (1, 1):
+        return None
+    if isinstance(conv, nn.ConvTranspose2d):
+        ok = conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.padding == (1, 1) and conv.output_padding == (1, 1)
+        return "deconv" if ok else None
+    if conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2)):
+        return "3x3"
+    if conv.kernel_size == (5, 5) and conv.padding == (2, 2) and conv.stride == (2, 2):
+        return "poly"
+    return None
+
+
+def _native_conv(x, x2, wpk, b, mode, c, relu):
+    """Run one folded conv on the C-ABI kernels; None when this channel combination has no kernel."""
+    if mode == "deconv":
+        if x2 is None and _ops.deconv3x3_supported(x.shape[1], wpk.shape[2]):
+            return _ops.deconv3x3(x, wpk, b, relu)
+        return None
+    if mode == "poly":
+        if x2 is None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and _ops.conv3x3_supported(4 * x.shape[1], 0, wpk.shape[2], 1):
+            return _ops.conv3x3(F.pixel_unshuffle(x, 2), None, wpk, b, relu, 1)
+        return None
+    stride = c.stride[0]
+    if x2 is None and x.shape[1] < 8 and wpk.shape[0] == 8:           # 3-channel image: zero-padded to one 8-channel chunk
+        x = F.pad(x, (0, 0, 0, 0, 0, 8 - x.shape[1]))
+    if _ops.conv3x3_supported(x.shape[1], 0 if x2 is None else x2.shape[1], wpk.shape[2], stride):
+        return _ops.conv3x3(x, x2, wpk, b, relu, stride)
+    return None
 
 
 def _folded(conv, bn):
-    """(weight, bias, packed weight | None) of conv followed by eval-mode BatchNorm (bn may be None: plain conv with
-    bias), cached on the conv module and rebuilt whenever any of the tensors involved is modified or moved."""
+    """(weight, bias, packed weight | None, native mode | None) of conv followed by eval-mode BatchNorm (bn may be None:
+    plain conv with bias), cached on the conv module and rebuilt whenever a tensor involved is modified or moved."""
     src = (conv.weight,) + ((bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else (conv.bias,))
     key = tuple((t.data_ptr(), t._version) for t in src)
     cache = conv.__dict__.get("_adamvs_folded")
@@ -81,10 +110,18 @@ def _folded(conv, bn):
                 b = (bn.bias - bn.running_mean * scale).contiguous()
             else:
                 w, b = conv.weight.detach().contiguous(), conv.bias.detach().contiguous()
-            wpk = _ops.pack_conv3x3_weight(w) if _is_plain_3x3(conv) else None
-        cache = (key, w, b, wpk)
+            mode = _conv_mode(conv)
+            wpk = None
+            if mode == "3x3":
+                wp = F.pad(w, (0, 0, 0, 0, 0, 8 - w.shape[1])) if w.shape[1] < 8 else w
+                wpk = _ops.pack_conv3x3_weight(wp)
+            elif mode == "poly":
+                wpk = _ops.pack_conv3x3_weight(_ops.polyphase_5x5_s2_weight(w))
+            elif mode == "deconv":
+                wpk = _ops.pack_deconv3x3_weight(w)
+        cache = (key, w, b, wpk, mode)
         conv.__dict__["_adamvs_folded"] = cache
-    return cache[1], cache[2], cache[3]
+    return cache[1], cache[2], cache[3], cache[4]
 
 
 class _UpFuse(nn.Module):
@@ -165,7 +202,11 @@ class CostRegNet2D(nn.Module):
         if self.training or not _FOLD_BN:
             return seq(x)
         c = seq[0]
-        w, b, _ = _folded(c, seq[1])
+        w, b, wpk, mode = _folded(c, seq[1])
+        if mode is not None and _NATIVE_CONV and x.is_cuda and x.dtype == torch.float32:
+            y = _native_conv(x, None, wpk, b, mode, c, True)
+            if y is not None:
+                return y
         return F.relu_(F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation))
 
     def forward(self, x):
@@ -176,10 +217,11 @@ class CostRegNet2D(nn.Module):
         y = e4 + self._up(self.conv7, y)
         y = e2 + self._up(self.conv9, y)
         y = e0 + self._up(self.conv11, y)
-        if not self.training and _NATIVE_CONV and y.is_cuda and y.dtype == torch.float32 and \
-                _ops.conv3x3_supported(y.shape[1], 0, self.prob.out_channels, 1):
-            w, b, wpk = _folded(self.prob, None)
-            return _ops.conv3x3(y, None, wpk, b, False, 1)
+        if not self.training and _NATIVE_CONV and y.is_cuda and y.dtype == torch.float32:
+            w, b, wpk, mode = _folded(self.prob, None)
+            out = _native_conv(y, None, wpk, b, mode, self.prob, False) if mode is not None else None
+            if out is not None:
+                return out
         return self.prob(y)
 
 

@@ -476,7 +476,8 @@ def test_conv_tile_configurations_forced(cfg):
 
 @pytest.mark.parametrize("ca,cb,cout,stride,relu,h,w", [
     (8, 0, 8, 1, True, 40, 64), (16, 0, 16, 1, True, 36, 52), (32, 0, 32, 1, True, 24, 32), (16, 16, 16, 1, True, 32, 64),
-    (8, 8, 8, 1, True, 64, 96), (48, 0, 48, 1, False, 24, 48), (48, 0, 48, 2, True, 24, 48), (48, 0, 48, 1, True, 18, 30)])
+    (8, 8, 8, 1, True, 64, 96), (48, 0, 48, 1, False, 24, 48), (48, 0, 48, 2, True, 24, 48), (48, 0, 48, 1, True, 18, 30),
+    (32, 0, 16, 1, True, 64, 96), (64, 0, 32, 1, True, 32, 48), (64, 0, 32, 1, True, 30, 44)])
 def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
     """The 3x3 convolutions of FeatureNet0 / CostRegNet2D on the FFMA kernels (TMA and generic-tile paths) against
     F.conv2d in fp32 on the CPU: same math, different summation order."""
@@ -492,4 +493,53 @@ def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
     got = ops.conv3x3(xa.to(_dev()), None if xb is None else xb.to(_dev()), ops.pack_conv3x3_weight(wt).to(_dev()),
                       bias.to(_dev()), relu, stride).cpu()
     assert tuple(got.shape) == tuple(want.shape)
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(32, 16, 12, 20), (16, 8, 24, 36), (48, 48, 6, 10)])
+def test_native_deconv3x3_vs_torch(cin, cout, h, w):
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cin, cout, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    want = F.relu(F.conv_transpose2d(x, wt, bias, stride=2, padding=1, output_padding=1))
+    got = ops.deconv3x3(x.to(_dev()), ops.pack_deconv3x3_weight(wt).to(_dev()), bias.to(_dev()), True).cpu()
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_feature_net_and_pair_unet_native_vs_oracle():
+    """FeatureNet0 and CostRegNet2D with every supported conv on the native kernels (3x3, polyphase 5x5 stride 2,
+    transposed, zero-padded 3-channel input) against the oracle's torch-CPU restatement of the reference."""
+    from adamvs_b200 import synth
+    import models.adamvs as M
+    sd = synth.fill_state_dict(synth.state_dict_shapes(48), 5)
+    imgs, _, _ = synth.make_sample(1, 128, 192, 5, seed=2)
+    m = _model("stream", sd, (48, 32, 8), 192)
+    want = O.feature_net(sd, imgs[0])
+    assert M._NATIVE_CONV
+    from adamvs_b200.cascade import _true_fp32            # the product runs the remaining cuDNN pieces with TF32 off
+    with torch.no_grad(), _true_fp32():
+        got = m.feature(imgs[0].to(_dev()))
+    for k in want:
+        assert abs_err(got[k].cpu(), want[k]) < 2e-5 * max(1.0, float(want[k].abs().max())), k
+    g = torch.Generator().manual_seed(3)
+    score = torch.randn(4, 48, 32, 48, generator=g)
+    with torch.no_grad(), _true_fp32():
+        got = m.DepthNet[0].reg(score.to(_dev())).cpu()
+    want = O.pair_unet(sd, "DepthNet.0.reg", score)
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(8, 16, 128, 192), (16, 32, 64, 96), (16, 32, 36, 52)])
+def test_polyphase_5x5_stride2_vs_torch(cin, cout, h, w):
+    """5x5 stride-2 convolution = pixel_unshuffle + 3x3 stride-1 convolution with re-laid weights, on the native kernel."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 5, 5, generator=g) / (5.0 * cin ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    want = F.relu(F.conv2d(x, wt, bias, 2, 2))
+    wpk = ops.pack_conv3x3_weight(ops.polyphase_5x5_s2_weight(wt)).to(_dev())
+    got = ops.conv3x3(F.pixel_unshuffle(x.to(_dev()), 2), None, wpk, bias.to(_dev()), True, 1).cpu()
     assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
