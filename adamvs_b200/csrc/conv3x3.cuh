@@ -176,7 +176,7 @@ conv3x3_kernel(ConvArgs a) {
                     }
                 } else if (EPI == EPI_CAND) {
                     const size_t o = ((size_t)b * COUT + co) * plane + pix;
-                    const float cand = tanhf(v + __ldg(a.bias + co));
+                    const float cand = tanh_f(v + __ldg(a.bias + co));
                     const float u = a.ugate[o];
                     a.out0[o] = u * a.hstate[o] + (1.f - u) * cand;
                 } else if (EPI == EPI_BIAS) {
@@ -222,7 +222,7 @@ struct V2Cfg {
     static constexpr int CHUNK_FLOATS = CKT * IH * IP;
     static constexpr int STEP_FLOATS = KSPLIT * CHUNK_FLOATS;
     static constexpr int NACC = PY * PX * COT;
-    static constexpr int RED_FLOATS = (KSPLIT - 1) * GROUP * NCOG * NACC;
+    static constexpr int RED_FLOATS = KSPLIT > 1 ? KSPLIT * GROUP * NCOG * NACC : 0;     // [slice][row,channel pair][px][thread]
     static constexpr int W_FLOATS = CIN * 9 * COB;
     static constexpr size_t SMEM = sizeof(float) * (size_t)(NSTAGE * STEP_FLOATS + W_FLOATS + RED_FLOATS) + 8 * NSTAGE;
     static_assert(NCHUNK % KSPLIT == 0, "KSPLIT must divide the chunk count");
@@ -241,7 +241,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sIn = reinterpret_cast<float*>(smem_raw);                 // [NSTAGE][KSPLIT][CKT][IH][IP]
     float* sW = sIn + NSTAGE * G::STEP_FLOATS;                       // [CIN][9][COB]
-    float* sRed = sW + G::W_FLOATS;                                  // [KSPLIT-1][NACC][GROUP*NCOG]
+    float* sRed = sW + G::W_FLOATS;                                  // [KSPLIT][PY*COT pairs][PX][GROUP*NCOG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + G::RED_FLOATS);
 
     const int tid = threadIdx.x;
@@ -365,33 +365,39 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncthreads();                           // slot consumed: the producer may refill it
         }
 
-        if (KSPLIT > 1) {                               // reduce the k-slices into slice 0
-            constexpr int GN = G::GROUP * G::NCOG;
-            if (ks > 0) {
-                float* dst = sRed + (size_t)(ks - 1) * G::NACC * GN + gt;
+        // Split-K reduction with a symmetric epilogue: the (row j, channel c) pairs of a thread's patch are dealt
+        // round-robin to the k-slices; every slice parks the partial sums of the pairs it does not own in shared
+        // memory and finishes (activation, state blend, store) the pairs it owns, so the epilogue - 64 transcendental
+        // evaluations per patch in the GRU layers - is shared by all warps instead of serialised on slice 0.
+        constexpr int GN = G::GROUP * G::NCOG;
+        if (KSPLIT > 1) {
 #pragma unroll
-                for (int j = 0; j < PY; ++j)
+            for (int j = 0; j < PY; ++j)
 #pragma unroll
-                    for (int p = 0; p < PX; ++p)
+                for (int c = 0; c < COT; ++c) {
+                    const int pair = j * COT + c;
+                    if (pair % KSPLIT == ks) continue;
+                    float* dst = sRed + ((size_t)(ks * (PY * COT) + pair) * PX) * GN + gt;
 #pragma unroll
-                        for (int c = 0; c < COT; ++c) dst[((j * PX + p) * COT + c) * GN] = acc[j][p][c];
-            }
-            __syncthreads();
-            if (ks == 0) {
-#pragma unroll
-                for (int s = 0; s < KSPLIT - 1; ++s) {
-                    const float* src = sRed + (size_t)s * G::NACC * GN + gt;
-#pragma unroll
-                    for (int j = 0; j < PY; ++j)
-#pragma unroll
-                        for (int p = 0; p < PX; ++p)
-#pragma unroll
-                            for (int c = 0; c < COT; ++c) acc[j][p][c] += src[((j * PX + p) * COT + c) * GN];
+                    for (int p = 0; p < PX; ++p) dst[p * GN] = acc[j][p][c];
                 }
-            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < PY; ++j)
+#pragma unroll
+                for (int c = 0; c < COT; ++c) {
+                    const int pair = j * COT + c;
+                    if (pair % KSPLIT != ks) continue;
+#pragma unroll
+                    for (int q = 0; q < KSPLIT; ++q) {
+                        if (q == ks) continue;
+                        const float* src = sRed + ((size_t)(q * (PY * COT) + pair) * PX) * GN + gt;
+#pragma unroll
+                        for (int p = 0; p < PX; ++p) acc[j][p][c] += src[p * GN];
+                    }
+                }
             // sRed is rewritten only after the next tile's steps, each of which ends in a __syncthreads
         }
-        if (ks != 0) continue;
 
         // -------------------------------------------------------------- epilogue (float4 along x)
         const int tile = blockIdx.x + ti * gridDim.x;
@@ -409,6 +415,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const size_t pix = (size_t)oy * a.wout + ox;
 #pragma unroll
                 for (int c = 0; c < COT; ++c) {
+                    if (KSPLIT > 1 && (j * COT + c) % KSPLIT != ks) continue;     // another slice finishes this pair
                     const int co = co_base + c;
                     float v[4] = {acc[j][0][c], acc[j][1][c], acc[j][2][c], acc[j][3][c]};
                     if (EPI == EPI_RELU) {
@@ -434,7 +441,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
                         const float uu[4] = {u.x, u.y, u.z, u.w}, hv[4] = {hh.x, hh.y, hh.z, hh.w};
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanhf(v[p] + bc);
+                        for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanh_f(v[p] + bc);
                         *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0], v[1], v[2], v[3]);
                     } else if (EPI == EPI_BIAS) {
                         const float bc = __ldg(a.bias + co);
@@ -519,7 +526,10 @@ struct RingDepth {
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
 struct ConvLayer {
     static constexpr int CIN = CA + CB, NCHUNK = CIN / CK;
-    static constexpr int KS_BIG = (COB == 8 && NCHUNK % 2 == 0) ? 2 : 1;      // 8-channel layers: two k-slices -> 4 warps
+    // 8-channel layers in the large configuration: 4x1 patches on the 32x16 tile (128 threads on one tile's worth of
+    // shared memory, 4 CTAs per SM) instead of 4x2 patches (64 threads) or split-K (whose two-step ring and reduction
+    // buffer cost 130 KB and left one CTA per SM: 332 us vs 244 us for the GRU-1 candidate conv, profiles/r01k)
+    static constexpr int PY_BIG = COB == 8 ? 1 : 2;
     // split-K factor of the small-plane configuration, bounded by shared memory: stride-2 boxes are 3x larger
     // (no split), 128 input channels keep 74 KB of weights resident (split by 2 at most)
     static constexpr int KS_SMALL = STRIDE == 2 ? 1 : ((NCHUNK % 4 == 0 && CIN < 128) ? 4 : (NCHUNK % 2 == 0 ? 2 : 1));
@@ -548,7 +558,7 @@ struct ConvLayer {
     }
     static cudaError_t launch(ConvPlan& p, int B, cudaStream_t st) {
         switch (p.cfg) {
-            case 0: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 16, 2, KS_BIG, CK, RingDepth<CIN, COB, STRIDE, 16, KS_BIG, NCHUNK / KS_BIG>::value>(p, B, st);
+            case 0: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 16, PY_BIG, 1, CK, RingDepth<CIN, COB, STRIDE, 16, 1, NCHUNK>::value>(p, B, st);
             case 1: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, 1, CK, RingDepth<CIN, COB, STRIDE, 8, 1, NCHUNK>::value>(p, B, st);
             default: return launch_v2<CA, CB, COUT, COB, STRIDE, EPI, 8, 1, KS_SMALL, CK, RingDepth<CIN, COB, STRIDE, 8, KS_SMALL, NCHUNK / KS_SMALL>::value>(p, B, st);
         }

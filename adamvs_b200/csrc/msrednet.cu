@@ -67,7 +67,7 @@ gn_cand_kernel(const float* __restrict__ o, const double* __restrict__ stats, co
     const float a = m.rstd * __ldg(g + c), cc = __ldg(bt + c) - m.mean * a;
     const size_t idx = ((size_t)b * HC + c) * hw + i;
     const float uv = u[idx];
-    h[idx] = uv * h[idx] + (1.f - uv) * tanhf(fmaf(o[idx], a, cc));
+    h[idx] = uv * h[idx] + (1.f - uv) * tanh_f(fmaf(o[idx], a, cc));
 }
 
 // ---- y = relu(convT3x3 s2 p1 op1 (inA [+ inB]; CIN -> COUT)), no bias (ConvTransReLU) -------------------
@@ -298,7 +298,7 @@ static int run_msred(const float* volume, const adamvs_msred_weights* wts, const
         ADAMVS_TRY((launch_upconv<16, 8>(ws.up2, ws.s[1], ws.pk_u1, ws.up1, B, hh[1], wwv[1], st)));
         if (int e = gru(Lg1, Lo1, 0, k, k)) return e;
         dim3 grid((w + 127) / 128, h, B);
-        out_conv_regress_kernel<<<grid, 128, 0, st>>>(ws.up1, ws.s[0], 1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+        out_conv_regress_kernel<true, true><<<grid, 128, 0, st>>>(ws.up1, ws.s[0], ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
         ADAMVS_TRY(cudaGetLastError());
     }
     return 0;

@@ -253,7 +253,7 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
         {
             dim3 grid((w + 127) / 128, h, B);
             if (out_up) out_upconv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
-            else out_conv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, nullptr, 0, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+            else out_conv_regress_kernel<false, false><<<grid, 128, 0, st>>>(ws.y, nullptr, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
         }
         ADAMVS_TRY(cudaGetLastError());
     }

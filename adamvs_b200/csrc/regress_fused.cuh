@@ -46,8 +46,9 @@ __device__ __forceinline__ void regress_update(const RegressState& st, size_t o,
 
 // logit = conv3x3(y [+ y2]; 8->1) + b at the same resolution.  `flip` reads the taps mirrored, which turns the
 // correlation into PyTorch's stride-1 ConvTranspose2d (MS-REDNet's output layer, models/msrednet.py:351).
+template <bool HAS_Y2, bool FLIP>
 static __global__ void __launch_bounds__(128)
-out_conv_regress_kernel(const float* __restrict__ y, const float* __restrict__ y2, int flip, OutWeights ow, HypSpec hs,
+out_conv_regress_kernel(const float* __restrict__ y, const float* __restrict__ y2, OutWeights ow, HypSpec hs,
                         int prob_mode, RegressState st,
                         float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
                         int k, int D, int h, int w) {
@@ -62,7 +63,7 @@ out_conv_regress_kernel(const float* __restrict__ y, const float* __restrict__ y
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) {
         const float* p = y + ((size_t)b * 8 + ci) * hw;
-        const float* p2 = y2 ? y2 + ((size_t)b * 8 + ci) * hw : nullptr;
+        const float* p2 = HAS_Y2 ? y2 + ((size_t)b * 8 + ci) * hw : nullptr;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int gy = yy + ky - 1;
@@ -72,9 +73,9 @@ out_conv_regress_kernel(const float* __restrict__ y, const float* __restrict__ y
                 const int gx = x + kx - 1;
                 if (gx < 0 || gx >= w) continue;
                 float v = __ldg(p + (size_t)gy * w + gx);
-                if (p2) v += __ldg(p2 + (size_t)gy * w + gx);
+                if (HAS_Y2) v += __ldg(p2 + (size_t)gy * w + gx);
                 const int tap = ky * 3 + kx;
-                acc = fmaf(v, sw[ci * 9 + (flip ? 8 - tap : tap)], acc);
+                acc = fmaf(v, sw[ci * 9 + (FLIP ? 8 - tap : tap)], acc);
             }
         }
     }
