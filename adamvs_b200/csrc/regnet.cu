@@ -86,6 +86,161 @@ upconv_add_relu_kernel(const float* __restrict__ in, const float* __restrict__ w
 }
 
 // ------------------------------------------------------------------------------------------------
+// 7+8 fused: y = relu(convT(h2) + b + h1) is produced per 32x16 tile (with the 1-pixel halo the output layer needs,
+// recomputed: 1.2x of a small layer) straight into shared memory and consumed there by the output layer and the
+// online regression; y never goes to global memory (saves a 32 B/px write and read per plane and one launch).
+//   UP = false (stage 3): logit = conv3x3(y) + b on the tile            -> y halo on all four sides
+//   UP = true  (stages 1-2): logit(2y+a, 2x+b) = convT3x3 s2 (y) + b     -> y halo on the right and bottom
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailW = 32, kTailH = 16;
+
+template <bool UP>
+struct TailGeom {
+    static constexpr int LO = UP ? 0 : 1;                       // halo before the tile
+    static constexpr int YH = kTailH + LO + 1, YW = kTailW + LO + 1;      // y rows / cols held (18x34 | 17x33)
+    static constexpr int YP = YW + 3;                            // pitch
+    static constexpr int QH = UP ? kTailH / 2 + 1 : kTailH / 2 + 2;       // half-resolution quads covering them (9 | 10)
+    static constexpr int QW = UP ? kTailW / 2 + 1 : kTailW / 2 + 2;       // (17 | 18)
+    static constexpr int HP = QW + 1 + 1;                        // h2 patch: QW + 1 columns, padded
+    static constexpr int HH = QH + 1;
+};
+
+template <bool UP>
+__global__ void __launch_bounds__(256)
+tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk_up, const float* __restrict__ up_b,
+                    const float* __restrict__ h1, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
+                    float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
+                    int k, int D, int h, int w) {
+    using G = TailGeom<UP>;
+    __shared__ float sH2[16 * G::HH * G::HP];
+    __shared__ float sY[8 * G::YH * G::YP];
+    __shared__ float sWu[16 * 9 * 8];
+    __shared__ float sWo[73];
+    const int tid = threadIdx.x;
+    const int tiles_x = (w + kTailW - 1) / kTailW;
+    const int ox0 = (blockIdx.x % tiles_x) * kTailW, oy0 = (blockIdx.x / tiles_x) * kTailH;
+    const int b = blockIdx.z;
+    const int h2 = h / 2, w2 = w / 2;
+    const size_t hw = (size_t)h * w, hw2 = (size_t)h2 * w2;
+    const int qy0 = oy0 / 2 - G::LO, qx0 = ox0 / 2 - G::LO;     // first half-resolution quad
+
+    for (int i = tid; i < 16 * 9 * 8; i += 256) sWu[i] = __ldg(wpk_up + i);
+    if (tid < 72) sWo[tid] = __ldg(ow.w + tid);
+    if (tid == 72) sWo[72] = __ldg(ow.b);
+    for (int i = tid; i < 16 * G::HH * (G::QW + 1); i += 256) {
+        const int cx = i % (G::QW + 1), rc = i / (G::QW + 1);
+        const int ry = rc % G::HH, c = rc / G::HH;
+        const int gy = qy0 + ry, gx = qx0 + cx;
+        float v = 0.f;
+        if (gy >= 0 && gy < h2 && gx >= 0 && gx < w2) v = __ldg(h2s + ((size_t)b * 16 + c) * hw2 + (size_t)gy * w2 + gx);
+        sH2[(c * G::HH + ry) * G::HP + cx] = v;
+    }
+    __syncthreads();
+
+    // ---- phase A: one half-resolution quad per thread -> 2x2 pixels x 8 channels of y
+    if (tid < G::QH * G::QW) {
+        const int qy = tid / G::QW, qx = tid - qy * G::QW;
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+#pragma unroll 4
+        for (int ci = 0; ci < 16; ++ci) {
+            const float* p = sH2 + (ci * G::HH + qy) * G::HP + qx;
+            const float v00 = p[0], v01 = p[1], v10 = p[G::HP], v11 = p[G::HP + 1];
+            const float* wt = sWu + ci * 72;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                acc[0][c] += v00 * wt[4 * 8 + c];
+                acc[1][c] += v01 * wt[3 * 8 + c] + v00 * wt[5 * 8 + c];
+                acc[2][c] += v10 * wt[1 * 8 + c] + v00 * wt[7 * 8 + c];
+                acc[3][c] += v11 * wt[0 * 8 + c] + v10 * wt[2 * 8 + c] + v01 * wt[6 * 8 + c] + v00 * wt[8 * 8 + c];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int fy = 2 * (qy0 + qy) + (q >> 1), fx = 2 * (qx0 + qx) + (q & 1);     // full-resolution pixel
+            const int ry = fy - (oy0 - G::LO), rx = fx - (ox0 - G::LO);                  // position inside sY
+            if (ry < 0 || ry >= G::YH || rx < 0 || rx >= G::YW) continue;
+            const bool in = fy >= 0 && fy < h && fx >= 0 && fx < w;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float v = 0.f;                                                            // outside the image: the output layer's zero padding
+                if (in) v = fmaxf(acc[q][c] + __ldg(up_b + c) + __ldg(h1 + ((size_t)b * 8 + c) * hw + (size_t)fy * w + fx), 0.f);
+                sY[(c * G::YH + ry) * G::YP + rx] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: output layer + online regression, two x-adjacent y pixels per thread
+    const int ty = tid / 16, tx = (tid % 16) * 2;
+    const int y0 = oy0 + ty;
+    if (y0 >= h) return;
+    if (!UP) {
+        float lg[2] = {sWo[72], sWo[72]};
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* p = sY + (ci * G::YH + ty + ky) * G::YP + tx;
+                const float v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+                const float* wt = sWo + ci * 9 + ky * 3;
+                lg[0] = fmaf(v0, wt[0], fmaf(v1, wt[1], fmaf(v2, wt[2], lg[0])));
+                lg[1] = fmaf(v1, wt[0], fmaf(v2, wt[1], fmaf(v3, wt[2], lg[1])));
+            }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x >= w) continue;
+            const int pix = y0 * w + x;
+            const size_t o = (size_t)b * hw + pix;
+            if (logits_out) logits_out[((size_t)b * D + k) * hw + pix] = lg[e];
+            regress_update(st, o, lg[e], hyp_at(hyp_line(hs, b, pix, (int)hw, D), k), k, D, prob_mode, depth, conf);
+        }
+    } else {
+        const int Ho = 2 * h, Wo = 2 * w;
+        const size_t ohw = (size_t)Ho * Wo;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x >= w) continue;
+            float l00 = sWo[72], l01 = sWo[72], l10 = sWo[72], l11 = sWo[72];
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const float* p = sY + (ci * G::YH + ty) * G::YP + tx + e;
+                const float v00 = p[0], v01 = p[1], v10 = p[G::YP], v11 = p[G::YP + 1];   // zero beyond the image (phase A)
+                const float* wt = sWo + ci * 9;
+                l00 += v00 * wt[4];
+                l01 += v01 * wt[3] + v00 * wt[5];
+                l10 += v10 * wt[1] + v00 * wt[7];
+                l11 += v11 * wt[0] + v10 * wt[2] + v01 * wt[6] + v00 * wt[8];
+            }
+            const float lg[4] = {l00, l01, l10, l11};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oy = 2 * y0 + (q >> 1), ox = 2 * x + (q & 1);
+                float dval;
+                if (hs.mode == ADAMVS_HYP_PLANES) {
+                    dval = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
+                } else {
+                    const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
+                    const float d00 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i0, (int)hw, D), k);
+                    const float d01 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i1, (int)hw, D), k);
+                    const float d10 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i0, (int)hw, D), k);
+                    const float d11 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i1, (int)hw, D), k);
+                    dval = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
+                }
+                const size_t o = (size_t)b * ohw + (size_t)oy * Wo + ox;
+                if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)oy * Wo + ox] = lg[q];
+                regress_update(st, o, lg[q], dval, k, D, prob_mode, depth, conf);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launch helpers (non-TMA fallback: any even h, w; fixed 16x16 tiles)
 // ------------------------------------------------------------------------------------------------
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TW, int TH>
@@ -244,16 +399,11 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
             ADAMVS_TRY((launch_conv_auto<16, 16, 32, 16, 1, EPI_GATES>(a5, B, st)));
             ADAMVS_TRY((launch_conv_auto<16, 16, 16, 16, 1, EPI_CAND>(a6, B, st)));
         }
-        // 7 up1 + skip + relu
+        // 7+8: up1 + skip + relu -> output layer -> online regression, one launch
         {
-            dim3 grid((w2 + 127) / 128, h2, B);
-            upconv_add_relu_kernel<16, 8><<<grid, 128, 0, st>>>(ws.h2, ws.pk_up1, hwts->up1_b, ws.h1, ws.y, h2, w2);
-        }
-        // 8 output layer + regression
-        {
-            dim3 grid((w + 127) / 128, h, B);
-            if (out_up) out_upconv_regress_kernel<<<grid, 128, 0, st>>>(ws.y, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
-            else out_conv_regress_kernel<false, false><<<grid, 128, 0, st>>>(ws.y, nullptr, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+            dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
+            if (out_up) tail_regress_kernel<true><<<grid, 256, 0, st>>>(ws.h2, ws.pk_up1, hwts->up1_b, ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+            else tail_regress_kernel<false><<<grid, 256, 0, st>>>(ws.h2, ws.pk_up1, hwts->up1_b, ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
         }
         ADAMVS_TRY(cudaGetLastError());
     }
