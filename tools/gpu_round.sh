@@ -19,6 +19,7 @@ benchms) python bench.py --model msrednet --steps 5 --warmup 3 --batch 4 > gpuru
 bench1) python bench.py --steps 10 --warmup 3 --batch 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_b1.json 2> gpurun_out/${TAG}_bench_b1.err; python tools/show_bench.py gpurun_out/${TAG}_bench_b1.json;;
 ncu_k2) ncu --set full --clock-control none --import-source on -k regex:'fused_volume_kernel|pair_score_kernel|warp_volume' -s 2 -c 10 -f -o gpurun_out/${TAG}_k2 \
     python tools/prof_kernels.py --batch 8 --only k1,k2 --iters 1 > gpurun_out/${TAG}_ncu_k2.log 2>&1; export_rep gpurun_out/${TAG}_k2;;
+ncu_k3s2) for S in 2; do ncu --set full --clock-control none --import-source on -k regex:"conv3x3|upconv|regress" -s 49 -c 7 -f -o gpurun_out/${TAG}_k3_s${S} python tools/prof_kernels.py --batch 8 --only k3 --stages $S --planes 3 --iters 1 > gpurun_out/${TAG}_ncu_k3_s${S}.log 2>&1; export_rep gpurun_out/${TAG}_k3_s${S}; done;;
 ncu_k3s3) for S in 3; do ncu --set full --clock-control none --import-source on -k regex:'conv3x3|upconv|regress' -s 56 -c 8 -f -o gpurun_out/${TAG}_k3_s${S} \
     python tools/prof_kernels.py --batch 8 --only k3 --stages $S --planes 3 --iters 1 > gpurun_out/${TAG}_ncu_k3_s${S}.log 2>&1; export_rep gpurun_out/${TAG}_k3_s${S}; done;;
 ncu_k3) for S in 3 2 1; do ncu --set full --clock-control none --import-source on -k regex:'conv3x3|upconv|regress' -s 56 -c 8 -f -o gpurun_out/${TAG}_k3_s${S} \
