@@ -21,7 +21,9 @@
 //   7 up1     y   = relu(convT3x3 s2 (h2) + b + h1)                      16 -> 8
 //   8 out     logit = convT3x3 s2 (y) + b  (stages 1-2) | conv3x3(y)+b (stage 3); online softmax update
 #include "conv3x3.cuh"
+#include "conv3x3_tc.cuh"
 #include "regress_fused.cuh"
+#include <string.h>
 
 namespace adamvs {
 
@@ -270,6 +272,12 @@ using Conv2 = ConvLayer<8, 0, 16, 16, 2, EPI_RELU>;
 using Gates2 = ConvLayer<16, 16, 32, 16, 1, EPI_GATES>;
 using Cand2 = ConvLayer<16, 16, 16, 16, 1, EPI_CAND>;
 template <int C> using Conv1 = ConvLayer<C, 0, 8, 8, 1, EPI_RELU>;
+// the same layers on the tensor cores (conv3x3_tc.cuh); conv2 (stride 2) and the tail stay on the FFMA kernels
+using TcGates1 = TcLayer<8, 8, 16, EPI_GATES>;
+using TcCand1 = TcLayer<8, 8, 8, EPI_CAND>;
+using TcGates2 = TcLayer<16, 16, 32, EPI_GATES>;
+using TcCand2 = TcLayer<16, 16, 16, EPI_CAND>;
+template <int C> using TcConv1 = TcLayer<C, 0, 8, EPI_RELU>;
 
 struct Workspace {
     float *pk_conv1, *pk_gates1, *pk_cand1, *pk_conv2, *pk_gates2, *pk_cand2, *pk_up1;
@@ -314,13 +322,37 @@ extern "C" size_t adamvs_regnet_red_workspace_floats(int B, int C, int D, int h,
 
 #define ADAMVS_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
+// Default arithmetic of adamvs_regnet_red_f32.  ADAMVS_K3_MATH=ffma|tc|tf32 is a test / measurement hook read once per
+// process (like ADAMVS_CONV_CFG); production callers pick a mode explicitly through adamvs_regnet_red_ex_f32.
+static int default_math() {
+    static const int m = [] {
+        const char* e = getenv("ADAMVS_K3_MATH");
+        if (e && !strcmp(e, "ffma")) return ADAMVS_MATH_FFMA;
+        if (e && !strcmp(e, "tc")) return ADAMVS_MATH_TC_FP32;
+        if (e && !strcmp(e, "tf32")) return ADAMVS_MATH_TC_TF32;
+        return ADAMVS_MATH_DEFAULT;
+    }();
+    return m;
+}
+
 extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_weights* hwts,
                                      int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
                                      int out_up, int prob_mode,
                                      float* workspace, size_t workspace_floats,
                                      float* depth, float* conf, float* logits_out,
                                      int B, int C, int D, int h, int w, void* stream) {
+    return adamvs_regnet_red_ex_f32(volume, hwts, hyp_mode, hyp_src, hyp_ncol, half_range, out_up, prob_mode, default_math(),
+                                    workspace, workspace_floats, depth, conf, logits_out, B, C, D, h, w, stream);
+}
+
+extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet_weights* hwts,
+                                        int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                                        int out_up, int prob_mode, int math_mode,
+                                        float* workspace, size_t workspace_floats,
+                                        float* depth, float* conf, float* logits_out,
+                                        int B, int C, int D, int h, int w, void* stream) {
     ADAMVS_CHECK_ARG(volume && hwts && workspace && depth && conf && hyp_src);
+    ADAMVS_CHECK_ARG(math_mode == ADAMVS_MATH_FFMA || math_mode == ADAMVS_MATH_TC_FP32 || math_mode == ADAMVS_MATH_TC_TF32);
     ADAMVS_CHECK_ARG(B > 0 && B <= 65535 && D >= 2 && h > 0 && w > 0 && (h % 2) == 0 && (w % 2) == 0 && h <= 65535);
     ADAMVS_CHECK_ARG(C == 8 || C == 16 || C == 32);
     ADAMVS_CHECK_ARG(prob_mode == ADAMVS_PROB_SOFTMAX || prob_mode == ADAMVS_PROB_EXP_EPS);
@@ -376,9 +408,28 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
                 && Gates2::plan(p5, a5, B, 1) && Cand2::plan(p6, a6, B, 1);
         tma = ok;
     }
+    // tensor-core layers need the TMA path; planes too small to fill the SMs stay on the split-K FFMA kernels
+    const bool tc = tma && math_mode != ADAMVS_MATH_FFMA;
+    const int prec = math_mode == ADAMVS_MATH_TC_TF32 ? PREC_TF32 : PREC_FP32X3;
+    ConvPlan q1, q2, q3, q5, q6;
+    if (tc) {
+        bool ok = (C == 8 ? TcConv1<8>::plan(q1, a1, B, D) : C == 16 ? TcConv1<16>::plan(q1, a1, B, D) : TcConv1<32>::plan(q1, a1, B, D));
+        ok = ok && TcGates1::plan(q2, a2, B, 1) && TcCand1::plan(q3, a3, B, 1) && TcGates2::plan(q5, a5, B, 1) && TcCand2::plan(q6, a6, B, 1);
+        if (!ok) return ADAMVS_EINVAL;
+    }
 
     for (int k = 0; k < D; ++k) {
-        if (tma) {
+        if (tc) {
+            q1.args.k = k;
+            if (C == 8) ADAMVS_TRY(TcConv1<8>::launch(q1, B, prec, st));
+            else if (C == 16) ADAMVS_TRY(TcConv1<16>::launch(q1, B, prec, st));
+            else ADAMVS_TRY(TcConv1<32>::launch(q1, B, prec, st));
+            ADAMVS_TRY(TcGates1::launch(q2, B, prec, st));
+            ADAMVS_TRY(TcCand1::launch(q3, B, prec, st));
+            ADAMVS_TRY(Conv2::launch(p4, B, st));
+            ADAMVS_TRY(TcGates2::launch(q5, B, prec, st));
+            ADAMVS_TRY(TcCand2::launch(q6, B, prec, st));
+        } else if (tma) {
             p1.args.k = k;
             if (C == 8) ADAMVS_TRY(Conv1<8>::launch(p1, B, st));
             else if (C == 16) ADAMVS_TRY(Conv1<16>::launch(p1, B, st));

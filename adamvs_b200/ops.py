@@ -19,10 +19,12 @@ HYP_PLANES, HYP_PER_PIXEL = 0, 1
 EPS_NUMERATOR, EPS_DENOMINATOR = 0, 1
 PROB_SOFTMAX, PROB_EXP_EPS = 0, 1
 INTERVAL_LAST_COLUMN, INTERVAL_FROM_RANGE = 0, 1
+MATH_FFMA, MATH_TC_FP32, MATH_TC_TF32 = 0, 1, 2
 
 EXPORTS = (
     "adamvs_abi_version", "adamvs_cascade_prepare", "adamvs_pair_score_f32", "adamvs_resize_bilinear_f32",
     "adamvs_fused_volume_f32", "adamvs_regnet_red_workspace_floats", "adamvs_regnet_red_f32",
+    "adamvs_regnet_red_ex_f32",
     "adamvs_softmax_regress_f32", "adamvs_variance_volume_f32", "adamvs_regnet_msred_workspace_floats",
     "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
     "adamvs_deconv3x3_supported", "adamvs_deconv3x3_f32",
@@ -65,6 +67,8 @@ def lib() -> ctypes.CDLL:
         L.adamvs_regnet_red_workspace_floats.restype = cs
         L.adamvs_regnet_red_f32.argtypes = [vp, ctypes.POINTER(RegnetWeights), ci, vp, ci, vp, ci, ci, vp, cs,
                                             vp, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_regnet_red_ex_f32.argtypes = [vp, ctypes.POINTER(RegnetWeights), ci, vp, ci, vp, ci, ci, ci, vp, cs,
+                                               vp, vp, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_softmax_regress_f32.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_variance_volume_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_regnet_msred_workspace_floats.argtypes = [ci, ci, ci, ci, ci]
@@ -222,9 +226,10 @@ def regnet_workspace_floats(B, C, D, h, w, out_up) -> int:
 
 
 def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob_mode: int,
-               workspace: Optional[torch.Tensor] = None, want_logits: bool = False):
+               workspace: Optional[torch.Tensor] = None, want_logits: bool = False, math: Optional[int] = None):
     """volume [B,C,D,h,w] -> depth, conf [B,Ho,Wo] (+ logits [B,D,Ho,Wo] when asked).
-    `weights`: name -> contiguous fp32 CUDA tensor in the reference layouts (see RegnetWeights)."""
+    `weights`: name -> contiguous fp32 CUDA tensor in the reference layouts (see RegnetWeights).
+    `math`: None = the library default, or MATH_FFMA / MATH_TC_FP32 / MATH_TC_TF32 (include/adamvs_b200.h)."""
     volume = _f32c(volume, "volume")
     B, C, D, h, w = volume.shape
     Ho, Wo = (2 * h, 2 * w) if out_up else (h, w)
@@ -237,9 +242,15 @@ def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob
     keep = {k: _f32c(v, k) for k, v in weights.items()}
     st = RegnetWeights(**{k: v.data_ptr() for k, v in keep.items()})
     with _timed("regnet_red", 7 + 7 * D):
-        _check(lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
-                                           _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
-                                           B, C, D, h, w, _stream()), "regnet_red")
+        if math is None:
+            rc = lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
+                                             _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
+                                             B, C, D, h, w, _stream())
+        else:
+            rc = lib().adamvs_regnet_red_ex_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode, int(math),
+                                                _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
+                                                B, C, D, h, w, _stream())
+        _check(rc, "regnet_red")
     return (depth, conf, logits) if want_logits else (depth, conf)
 
 

@@ -113,6 +113,25 @@ int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_weights* host
                           float* depth, float* conf, float* logits_out,
                           int B, int C, int D, int h, int w, void* stream);
 
+/* Arithmetic of the regulariser's 3x3 convolutions.
+ *   FFMA     fp32 FFMA direct convolutions.
+ *   TC_FP32  tcgen05.mma kind::tf32 with exact hi/lo operand splits (all four partial products, fp32 accumulation in
+ *            TMEM): fp32 accuracy, same tolerance as FFMA.
+ *   TC_TF32  activations rounded to tf32 (one pass), weights still split: reported separately with its own tolerance.
+ * Planes whose width is not a multiple of 8 fall back to FFMA in every mode. */
+#define ADAMVS_MATH_FFMA    0
+#define ADAMVS_MATH_TC_FP32 1
+#define ADAMVS_MATH_TC_TF32 2
+#define ADAMVS_MATH_DEFAULT ADAMVS_MATH_FFMA
+
+/* adamvs_regnet_red_f32 with an explicit arithmetic mode (adamvs_regnet_red_f32 uses ADAMVS_MATH_DEFAULT). */
+int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet_weights* host_weights,
+                             int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                             int out_up, int prob_mode, int math_mode,
+                             float* workspace, size_t workspace_floats,
+                             float* depth, float* conf, float* logits_out,
+                             int B, int C, int D, int h, int w, void* stream);
+
 /* K4 standalone — softmax over D + expectation + max for a materialised logit volume (the stage-1
  * pair branch: adamvs.py:274-283 / 481-489).  logits: [N,D,h,w]; hypothesis batch index = n / n_per_batch;
  * depth, conf: [N,h,w]. Hypotheses are taken at the logits' own resolution. */
