@@ -17,14 +17,16 @@
 // PREC_TF32 drops the A_lo pass (activations rounded to tf32, weights still exact): half the MMA time, reported
 // separately with its own tolerance.
 //
-// Warp-specialised persistent CTA (one per SM, 192 threads), static round-robin tile schedule:
-//   warp 4 lane 0   TMA producer: planar [8 ch][TH+2][40] boxes (halo zero-filled = conv padding) into a slot ring
-//   warps 0-3       converters: planar slot -> hi/lo quad-interleaved operand stage (LDS.32 x4 -> 2 STS.128 per
-//                   position, conflict-free), then the epilogue of the PREVIOUS tile (tcgen05.ld of their TMEM lane
-//                   quarter, bias + gate non-linearity + GRU blend, coalesced row stores) while the MMAs of the
-//                   current tile run
-//   warp 5 lane 0   MMA issuer: waits for operand stages, issues MT*9*{hi,lo} MMAs per chunk, tcgen05.commit hands the
+// Warp-specialised persistent CTA (one per SM, 320 threads), static round-robin tile schedule:
+//   warp 8 lane 0   TMA producer: planar [8 ch][TH+2][40] boxes (halo zero-filled = conv padding) into a slot ring
+//   warps 4-7       converters: planar slot -> hi/lo quad-interleaved operand stage (LDS.32 x4 -> 2 STS.128 per
+//                   position, conflict-free)
+//   warp 9 lane 0   MMA issuer: waits for operand stages, issues MT*9*{hi,lo} MMAs per chunk, tcgen05.commit hands the
 //                   stage back to the converters and, after a tile's last chunk, the accumulator to the epilogue
+//   warps 0-3       epilogue of the PREVIOUS tile while the MMAs of the current tile run: tcgen05.ld of their TMEM lane
+//                   quarter; the GRU state / gate operands are requested before the accumulators are awaited (one
+//                   round trip per 16 channels instead of one per value), bias + gate non-linearity + GRU blend,
+//                   coalesced row stores
 // Accumulators are double buffered in TMEM (2 x MT x 2*Cout columns).
 #pragma once
 #include "conv3x3.cuh"
@@ -107,26 +109,31 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = NHL * 2 * PLANE_BYTES;      // [hi|lo][2 quads][NPOS][4]
     static constexpr int B_STEP_BYTES = 2 * NB * 16;               // [2 quads][NB rows][4]
     static constexpr int B_BYTES = 9 * NCH * B_STEP_BYTES;
-    static constexpr int NSLOT = 2;                                // planar TMA ring
     static constexpr int SLOT_BYTES = G::BOX_FLOATS * 4;
-    static constexpr int BUDGET = 227 * 1024 - 256 - B_BYTES - NSLOT * SLOT_BYTES;
-    static constexpr int NA_FIT = BUDGET / STAGE_BYTES;
-    static constexpr int NA = NA_FIT > 4 ? 4 : NA_FIT;             // operand stages
+    // two operand stages (the converters fill one while the MMAs read the other; a conversion is several times
+    // shorter than a stage's MMAs); everything left goes to the planar TMA ring, whose depth is what hides the
+    // DRAM latency of the boxes (measured with a 2-deep ring: MMAs idle 75 % of the time, profiles/r01q)
+    static constexpr int NA = 2;
+    static constexpr int BUDGET = 227 * 1024 - 512 - B_BYTES - NA * STAGE_BYTES;
+    static constexpr int NSLOT_FIT = BUDGET / SLOT_BYTES;
+    static constexpr int NSLOT = NSLOT_FIT > 6 ? 6 : NSLOT_FIT;    // planar TMA ring
     static constexpr int ACC_COLS = MT * NB;                       // TMEM columns of one accumulator buffer
     static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
     static constexpr int NBAR = 2 * NSLOT + 2 * NA + 4;
     static constexpr size_t SMEM = (size_t)NSLOT * SLOT_BYTES + (size_t)NA * STAGE_BYTES + B_BYTES + 8 * NBAR + 16;
     static_assert(CA % CK == 0 && CB % CK == 0, "channel groups must be chunk aligned");
     static_assert(NB % 16 == 0 && NB <= 256, "M = 128 MMAs need N % 16 == 0");
-    static_assert(NA >= 2, "needs two operand stages");
+    static_assert(NSLOT >= 2, "needs a TMA ring of at least two boxes");
     static_assert(2 * ACC_COLS <= 512, "does not fit TMEM");
     static_assert(SMEM <= 227 * 1024, "does not fit shared memory");
     // one CTA per SM is what keeps a 512-column allocation from blocking a co-resident CTA forever
     static_assert(TMEM_COLS <= 256 || SMEM > 114 * 1024, "512-column configurations must be alone on their SM");
 };
 
+constexpr int kTcThreads = 320;     // warps 0-3 epilogue (TMEM lane quarters 0-3), 4-7 converters, 8 TMA producer, 9 MMA issuer
+
 template <int CA, int CB, int COUT, int EPI, int MT, int PREC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs a, TileGrid tg) {
     using C = TcCfg<CA, CB, COUT, MT, PREC>;
     using G = TcGeom<MT>;
@@ -142,9 +149,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* d_full = a_empty + C::NA;
     uint64_t* d_empty = d_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    __shared__ float sBias[COUT];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -154,8 +162,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
         fence_mbar_init();
     }
+    if (tid < COUT) sBias[tid] = (EPI == EPI_RELU || a.bias == nullptr) ? 0.f : __ldg(a.bias + tid);
     // resident weights: [ci][tap][co] -> B operand [tap][chunk][quad][W_hi co | W_lo co][4 ci], split once per CTA
-    for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += 192) {
+    for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += kTcThreads) {
         const int j = i & 3, n = (i >> 2) % COUT, kq = (i / (4 * COUT)) & 1, s = (i / (8 * COUT)) % C::NCH, t = i / (8 * COUT * C::NCH);
         const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + t) * COUT + n);
         float hi, lo;
@@ -165,7 +174,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         dst[(COUT + n) * 4 + j] = lo;
     }
     // positions past the tile are read only by garbage rows of D; give them finite values once
-    for (int i = tid; i < C::NA * C::STAGE_BYTES / 16; i += 192) reinterpret_cast<float4*>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < C::NA * C::STAGE_BYTES / 16; i += kTcThreads) reinterpret_cast<float4*>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -176,7 +185,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int total = my_tiles * C::NCH;                                      // chunk stream of this CTA
     const int tiles_per_item = tg.tiles_x * tg.tiles_y;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===== TMA producer
         if (lane == 0) {
             for (int g = 0; g < total; ++g) {
@@ -192,7 +201,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_4d(sSlot + slot * C::SLOT_BYTES, fromA ? &tmA : &tmB, &slot_full[slot], ox0 - 4, oy0 - 1, fromA ? a.k : 0, plane);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(C::NB);
@@ -227,89 +236,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 umma_commit(&d_full[acc]);                                     // accumulator complete
             }
         }
-    } else {
-        // ===== converters + epilogue (warps 0-3 = TMEM lane quarters 0-3)
-        const size_t plane = (size_t)a.hout * a.wout;
-        auto epilogue = [&](int ti) {
-            const int acc = ti & 1;
-            mbar_wait_bounded(&d_full[acc], (ti >> 1) & 1);
-            tc_fence_after();
-            const int tile = blockIdx.x + ti * gridDim.x;
-            const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
-            const int ox0 = (rr % tg.tiles_x) * G::TW, oy0 = (rr / tg.tiles_x) * G::TH;
-#pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const int m = mt * 128 + warp * 32 + lane;
-                const int ry = m / G::IPO, rx = m - ry * G::IPO;
-                const int oy = oy0 + ry, ox = ox0 + rx;
-                const bool valid = ry < G::TH && rx < G::TW && oy < a.hout && ox < a.wout;
-                const size_t pix = valid ? (size_t)oy * a.wout + ox : 0;
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
-                constexpr int CG = COUT < 16 ? COUT : 16;                    // output channels per TMEM load pair
-#pragma unroll 1
-                for (int c0 = 0; c0 < COUT; c0 += CG) {
-                    uint32_t rh[16], rl[16];
-                    float v[CG];
-                    if (COUT >= 16) {
-                        tmem_ld16_issue(taddr + c0, rh);                       // columns of A x W_hi
-                        tmem_ld16_issue(taddr + COUT + c0, rl);                // columns of A x W_lo
-                        tmem_ld_wait();
+    } else if (warp >= 4) {
+        // ===== converters: planar TMA slot -> hi/lo quad-interleaved operand stage
+        const int ct = tid - 128;
+        constexpr int NPP = G::IH * G::IPO;                                  // positions of one quad plane
+        constexpr int NJ = (NPP + 127) / 128;
+        int soff[NJ];                                                        // planar offset of this thread's j-th position
 #pragma unroll
-                        for (int c = 0; c < CG; ++c) v[c] = __uint_as_float(rh[c]) + __uint_as_float(rl[c]);
-                    } else {                                                   // COUT == 8: both halves in one 16-column load
-                        tmem_ld16_issue(taddr, rh);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int c = 0; c < CG; ++c) v[c] = __uint_as_float(rh[c]) + __uint_as_float(rh[COUT + c]);
-                    }
-                    if (!valid) continue;
-#pragma unroll
-                    for (int c = 0; c < CG; ++c) {
-                        const int co = c0 + c;
-                        if (EPI == EPI_GATES) {
-                            constexpr int HC = COUT / 2;
-                            const float s = sigmoid_f(v[c] + __ldg(a.bias + co));
-                            if (co < HC) {                                     // reset gate -> r*h
-                                const size_t o = ((size_t)b * HC + co) * plane + pix;
-                                a.out0[o] = s * a.hstate[o];
-                            } else {
-                                a.out1[((size_t)b * HC + (co - HC)) * plane + pix] = s;
-                            }
-                        } else if (EPI == EPI_CAND) {
-                            const size_t o = ((size_t)b * COUT + co) * plane + pix;
-                            const float u = a.ugate[o];
-                            a.out0[o] = u * a.hstate[o] + (1.f - u) * tanh_f(v[c] + __ldg(a.bias + co));
-                        } else if (EPI == EPI_RELU) {
-                            a.out0[((size_t)b * COUT + co) * plane + pix] = fmaxf(v[c], 0.f);
-                        } else {                                               // EPI_BIAS
-                            const float y = v[c] + __ldg(a.bias + co);
-                            a.out0[((size_t)b * COUT + co) * plane + pix] = a.relu ? fmaxf(y, 0.f) : y;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[acc]);
-        };
-
-        constexpr int EPI_AT = C::NCH > 1 ? 1 : 0;                           // previous tile's epilogue goes after this chunk
-        constexpr int NITEM = 2 * G::IH * G::IPO;                            // (quad, position) pairs of one chunk
-        int g = 0;
+        for (int j = 0; j < NJ; ++j) {
+            const int pos = ct + 128 * j, r = pos / G::IPO, col = pos - r * G::IPO;
+            soff[j] = r * G::BOXW + col + 3;
+        }
 #pragma unroll 1
-        for (int ti = 0; ti < my_tiles; ++ti) {
-#pragma unroll 1
-            for (int c = 0; c < C::NCH; ++c, ++g) {
-                const int slot = g % C::NSLOT, st = g % C::NA;
-                mbar_wait_bounded(&slot_full[slot], (g / C::NSLOT) & 1);
-                if (g >= C::NA) mbar_wait_bounded(&a_empty[st], ((g / C::NA) - 1) & 1);
-                const float* pl = reinterpret_cast<const float*>(sSlot + slot * C::SLOT_BYTES);
-                unsigned char* stage = sA + (size_t)st * C::STAGE_BYTES;
-#pragma unroll 3
-                for (int i = tid; i < NITEM; i += 128) {
-                    const int q = i / (G::IH * G::IPO), pos = i - q * (G::IH * G::IPO);
-                    const int r = pos / G::IPO, col = pos - r * G::IPO;
-                    const float* src = pl + (q * 4 * G::IH + r) * G::BOXW + col + 3;
+        for (int g = 0; g < total; ++g) {
+            const int slot = g % C::NSLOT, st = g % C::NA;
+            mbar_wait_bounded(&slot_full[slot], (g / C::NSLOT) & 1);
+            if (g >= C::NA) mbar_wait_bounded(&a_empty[st], ((g / C::NA) - 1) & 1);
+            const float* pl = reinterpret_cast<const float*>(sSlot + slot * C::SLOT_BYTES);
+            unsigned char* stage = sA + (size_t)st * C::STAGE_BYTES;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int pos = ct + 128 * j;
+                    if (j == NJ - 1 && pos >= NPP) break;
+                    const float* src = pl + q * 4 * G::IH * G::BOXW + soff[j];
                     const float e0 = src[0], e1 = src[G::IH * G::BOXW], e2 = src[2 * G::IH * G::BOXW], e3 = src[3 * G::IH * G::BOXW];
                     float4 h4, l4;
                     split_tf32(e0, h4.x, l4.x); split_tf32(e1, h4.y, l4.y); split_tf32(e2, h4.z, l4.z); split_tf32(e3, h4.w, l4.w);
@@ -317,18 +268,107 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     *dst = h4;
                     if (PREC == PREC_FP32X3) *(dst + 2 * G::NPOS) = l4;
                 }
-                fence_proxy_async();                                           // operand writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&a_full[st]); mbar_arrive(&slot_empty[slot]); }
-                if (c == EPI_AT && ti > 0) epilogue(ti - 1);
             }
+            fence_proxy_async();                                               // operand writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&a_full[st]); mbar_arrive(&slot_empty[slot]); }
         }
-        if (my_tiles > 0) epilogue(my_tiles - 1);
+    } else {
+        // ===== epilogue (warps 0-3 = TMEM lane quarters 0-3): runs one tile behind the MMAs
+        const size_t plane = (size_t)a.hout * a.wout;
+        constexpr int CG = COUT < 16 ? COUT : 16;                            // output channels per TMEM load pair
+        constexpr int NCG = COUT / CG, NG = MT * NCG;                        // (M tile, channel group) steps per tile
+        constexpr int HC = COUT / 2;
+#pragma unroll 1
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int acc = ti & 1;
+            const int tile = blockIdx.x + ti * gridDim.x;
+            const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
+            const int ox0 = (rr % tg.tiles_x) * G::TW, oy0 = (rr / tg.tiles_x) * G::TH;
+            auto geom = [&](int mt, bool& valid, size_t& pix) {
+                const int m = mt * 128 + warp * 32 + lane;
+                const int ry = m / G::IPO, rx = m - ry * G::IPO;
+                const int oy = oy0 + ry, ox = ox0 + rx;
+                valid = ry < G::TH && rx < G::TW && oy < a.hout && ox < a.wout;
+                pix = valid ? (size_t)oy * a.wout + ox : 0;
+            };
+            // GRU state / gate operands of step gi: requested one step ahead (the first step's before the accumulator
+            // is awaited), so their DRAM latency overlaps the MMAs / the previous step instead of stalling every step
+            auto preload = [&](int gi, float (&hs)[CG], float (&us)[CG]) {
+                if (EPI != EPI_GATES && EPI != EPI_CAND) return;
+                const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
+                bool valid; size_t pix;
+                geom(mt, valid, pix);
+                if (EPI == EPI_GATES) {
+#pragma unroll
+                    for (int c = 0; c < CG; ++c)
+                        hs[c] = (valid && c0 + c < HC) ? __ldg(a.hstate + ((size_t)b * HC + c0 + c) * plane + pix) : 0.f;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CG; ++c) {
+                        const size_t o = ((size_t)b * COUT + c0 + c) * plane + pix;
+                        us[c] = valid ? __ldg(a.ugate + o) : 0.f;
+                        hs[c] = valid ? a.hstate[o] : 0.f;
+                    }
+                }
+            };
+            auto process = [&](int gi, const float (&hs)[CG], const float (&us)[CG]) {
+                const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
+                bool valid; size_t pix;
+                geom(mt, valid, pix);
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
+                uint32_t rh[16], rl[16];
+                float v[CG];
+                if (COUT >= 16) {
+                    tmem_ld16_issue(taddr + c0, rh);                           // columns of A x W_hi
+                    tmem_ld16_issue(taddr + COUT + c0, rl);                    // columns of A x W_lo
+                } else {                                                       // COUT == 8: both halves in one 16-column load
+                    tmem_ld16_issue(taddr, rh);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < CG; ++c)
+                    v[c] = COUT >= 16 ? __uint_as_float(rh[c]) + __uint_as_float(rl[c]) : __uint_as_float(rh[c]) + __uint_as_float(rh[(COUT + c) & 15]);
+                if (!valid) return;
+#pragma unroll
+                for (int c = 0; c < CG; ++c) {
+                    const int co = c0 + c;
+                    if (EPI == EPI_GATES) {
+                        const float s = sigmoid_f(v[c] + sBias[co]);
+                        if (co < HC) a.out0[((size_t)b * HC + co) * plane + pix] = s * hs[c];      // reset gate -> r*h
+                        else a.out1[((size_t)b * HC + (co - HC)) * plane + pix] = s;
+                    } else if (EPI == EPI_CAND) {
+                        a.out0[((size_t)b * COUT + co) * plane + pix] = us[c] * hs[c] + (1.f - us[c]) * tanh_f(v[c] + sBias[co]);
+                    } else if (EPI == EPI_RELU) {
+                        a.out0[((size_t)b * COUT + co) * plane + pix] = fmaxf(v[c], 0.f);
+                    } else {                                                   // EPI_BIAS
+                        const float y = v[c] + sBias[co];
+                        a.out0[((size_t)b * COUT + co) * plane + pix] = a.relu ? fmaxf(y, 0.f) : y;
+                    }
+                }
+            };
+            float hs0[CG], us0[CG], hs1[CG], us1[CG];
+            preload(0, hs0, us0);
+            mbar_wait_bounded(&d_full[acc], (ti >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int gi = 0; gi < NG; gi += 2) {
+                if (gi + 1 < NG) preload(gi + 1, hs1, us1);
+                process(gi, hs0, us0);
+                if (gi + 1 < NG) {
+                    if (gi + 2 < NG) preload(gi + 2, hs0, us0);
+                    process(gi + 1, hs1, us1);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[acc]);
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
 }
 
 template <int CA, int CB, int COUT, int EPI>
@@ -365,7 +405,7 @@ struct TcLayer {
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
-        kern<<<dim3(ctas, 1, 1), 192, C::SMEM, st>>>(p.tA, p.tB, p.args, p.tg);
+        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.tA, p.tB, p.args, p.tg);
         return cudaGetLastError();
     }
     static cudaError_t launch(ConvPlan& p, int B, int prec, cudaStream_t st) {

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "tma.cuh"
 #include <limits.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace adamvs {
@@ -169,6 +170,11 @@ constexpr int kBW = 64, kBH = 12;          // source box per (view, channel).  T
                                             // words); a 16x2 warp shape with pitch 48 measured no better (profiles/r01f).
 constexpr int kBox = kBW * kBH;
 constexpr int kCK = 4;                      // channels per pipeline stage
+// Rough depth (an untrained or noisy previous stage, oblique geometry) spreads a tile's footprint over more source
+// rows.  The stage buffer is re-cut at run time, per block, into fewer channels of taller boxes: configuration j holds
+// kCK >> j channels of kBH << j rows per view (4x12, 2x24, 1x48) - same bytes, same occupancy, same gather code with
+// another channel stride - and only blocks whose footprint exceeds 64 x 48 texels take the global-gather path.
+constexpr int kNCfg = 3;
 constexpr int kKC = 4;                      // depth planes per block
 constexpr int kPX = 32, kPY = 8;            // pixel tile
 constexpr int kWvThreads = kPX * kPY;
@@ -272,11 +278,11 @@ __device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x
 
 template <int C, int VS, int MODE>
 __global__ void __launch_bounds__(kWvThreads, 2)
-warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, int nk) {
+warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                       const __grid_constant__ CUtensorMap tm2, WarpVolArgs a, int nk, int force_cfg) {
     constexpr int V = VS + 1;
-    constexpr int NCH = C / kCK;
     constexpr int STAGE = VS * kCK * kBox;             // floats per pipeline stage
-    static_assert(C % kCK == 0, "channel count must be a multiple of the stage depth");
+    static_assert(C % (2 * kCK) == 0, "the stage loop is unrolled by the two pipeline buffers");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sbuf = reinterpret_cast<float*>(smem_raw);                  // [2][VS][kCK][kBH][kBW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbuf + 2 * STAGE);    // [2]
@@ -331,15 +337,19 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
     __syncthreads();
     int bx[VS], by[VS];
     bool fits = true;
+    int rows = 0;                                      // source rows the tallest view footprint needs
 #pragma unroll
     for (int v = 0; v < VS; ++v) {
         const int mnx = sbox[v * 4 + 0], mny = sbox[v * 4 + 1], mxx = sbox[v * 4 + 2], mxy = sbox[v * 4 + 3];
         const bool any = mnx != INT_MAX;
         bx[v] = any ? (mnx & ~3) : 0;                  // TMA: innermost start coordinate 16-byte aligned
         by[v] = any ? mny : 0;
-        fits = fits && (!any || ((mxx + 1 - bx[v] < kBW) && (mxy + 1 - by[v] < kBH)));
+        fits = fits && (!any || (mxx + 1 - bx[v] < kBW));
+        rows = max(rows, any ? mxy + 2 - by[v] : 0);
     }
-    if (!fits) {                                       // block-uniform
+    int cfg = rows <= kBH ? 0 : (rows <= 2 * kBH ? 1 : 2);
+    if (force_cfg > 0 && force_cfg < kNCfg && cfg < force_cfg) cfg = force_cfg;     // test hook: exercise the tall-box cuts
+    if (!fits || rows > (kBH << (kNCfg - 1)) || force_cfg >= kNCfg) {               // block-uniform
         if (inside) warp_volume_slow<C, VS, MODE>(a, b, x, y, k0);
         return;
     }
@@ -352,15 +362,6 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
         }
 
     // ---- phase 2: double-buffered channel stages
-    auto issue = [&](int ch) {
-        const int s = ch & 1;
-        fence_proxy_async();
-        mbar_expect_tx(&bars[s], STAGE * 4);
-#pragma unroll
-        for (int v = 0; v < VS; ++v)
-            tma_load_4d(sbuf + s * STAGE + v * kCK * kBox, &tm, &bars[s], bx[v], by[v], 0, (b * V + v + 1) * C + ch * kCK);
-    };
-    if (tid == 0) issue(0);
     const float* ref = a.feat + ((size_t)b * V) * C * hw + pix;
     // per-thread gather bases: every tap address below is base + compile-time constant (stage, view, channel, corner)
     const float* tap[kKC][VS];
@@ -381,59 +382,77 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm, WarpVolArgs a, in
 #pragma unroll
     for (int kk = 0; kk < kKC; ++kk) kvalid[kk] = inside && (k0 + kk < a.D);
 
-    auto stage_body = [&](auto stage_tag, int ch) {
-        constexpr int S = decltype(stage_tag)::value;
-        if (tid == 0 && ch + 1 < NCH) issue(ch + 1);
-        float rc[kCK];
+    auto run = [&](auto cfg_tag) {
+        constexpr int CFG = decltype(cfg_tag)::value;
+        constexpr int CKc = kCK >> CFG;                // channels per stage
+        constexpr int CBOX = kBox << CFG;              // floats per (view, channel) box
+        constexpr int NCH = C / CKc;
+        const CUtensorMap* tm = CFG == 0 ? &tm0 : (CFG == 1 ? &tm1 : &tm2);
+        auto issue = [&](int ch) {
+            const int s = ch & 1;
+            fence_proxy_async();
+            mbar_expect_tx(&bars[s], STAGE * 4);
 #pragma unroll
-        for (int cc = 0; cc < kCK; ++cc) rc[cc] = inside ? __ldg(ref + (size_t)(ch * kCK + cc) * hw) : 0.f;
-        mbar_wait(&bars[S], (ch >> 1) & 1);
+            for (int v = 0; v < VS; ++v)
+                tma_load_4d(sbuf + s * STAGE + v * kCK * kBox, tm, &bars[s], bx[v], by[v], 0, (b * V + v + 1) * C + ch * CKc);
+        };
+        if (tid == 0) issue(0);
+        auto stage_body = [&](auto stage_tag, int ch) {
+            constexpr int S = decltype(stage_tag)::value;
+            if (tid == 0 && ch + 1 < NCH) issue(ch + 1);
+            float rc[CKc];
 #pragma unroll
-        for (int cc = 0; cc < kCK; ++cc) {
+            for (int cc = 0; cc < CKc; ++cc) rc[cc] = inside ? __ldg(ref + (size_t)(ch * CKc + cc) * hw) : 0.f;
+            mbar_wait(&bars[S], (ch >> 1) & 1);
 #pragma unroll
-            for (int kk = 0; kk < kKC; ++kk) {
-                // one independent 4-tap chain per view (ILP), combined afterwards
-                float sv[VS];
+            for (int cc = 0; cc < CKc; ++cc) {
 #pragma unroll
-                for (int v = 0; v < VS; ++v) {
-                    const float* p = tap[kk][v] + (S * STAGE + (v * kCK + cc) * kBox);
-                    float t = wt[kk][v][0] * p[0];
-                    t = fmaf(wt[kk][v][1], p[1], t);
-                    t = fmaf(wt[kk][v][2], p[kBW], t);
-                    sv[v] = fmaf(wt[kk][v][3], p[kBW + 1], t);
-                }
-                if (MODE == MODE_SCORE) {
+                for (int kk = 0; kk < kKC; ++kk) {
+                    // one independent 4-tap chain per view (ILP), combined afterwards
+                    float sv[VS];
 #pragma unroll
-                    for (int v = 0; v < VS; ++v)
-                        acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] =
-                            fmaf(rc[cc], sv[v], acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0]);
-                } else {
-                    float r;
-                    if (MODE == MODE_FUSED) {
-                        float sacc = sv[0];
-#pragma unroll
-                        for (int v = 1; v < VS; ++v) sacc += sv[v];
-                        r = fmaf(rc[cc], sacc, start) * inv;
-                    } else {
-                        float sum = rc[cc], sq = rc[cc] * rc[cc];
-#pragma unroll
-                        for (int v = 0; v < VS; ++v) { sum += sv[v]; sq = fmaf(sv[v], sv[v], sq); }
-                        const float m = sum / (float)V;
-                        r = sq / (float)V - m * m;
+                    for (int v = 0; v < VS; ++v) {
+                        const float* p = tap[kk][v] + (S * STAGE + v * kCK * kBox + cc * CBOX);
+                        float t = wt[kk][v][0] * p[0];
+                        t = fmaf(wt[kk][v][1], p[1], t);
+                        t = fmaf(wt[kk][v][2], p[kBW], t);
+                        sv[v] = fmaf(wt[kk][v][3], p[kBW + 1], t);
                     }
-                    st_cs_pred(outp + (size_t)cc * plane_stride + (size_t)kk * hw, r, kvalid[kk]);
+                    if (MODE == MODE_SCORE) {
+#pragma unroll
+                        for (int v = 0; v < VS; ++v)
+                            acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] =
+                                fmaf(rc[cc], sv[v], acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0]);
+                    } else {
+                        float r;
+                        if (MODE == MODE_FUSED) {
+                            float sacc = sv[0];
+#pragma unroll
+                            for (int v = 1; v < VS; ++v) sacc += sv[v];
+                            r = fmaf(rc[cc], sacc, start) * inv;
+                        } else {
+                            float sum = rc[cc], sq = rc[cc] * rc[cc];
+#pragma unroll
+                            for (int v = 0; v < VS; ++v) { sum += sv[v]; sq = fmaf(sv[v], sv[v], sq); }
+                            const float m = sum / (float)V;
+                            r = sq / (float)V - m * m;
+                        }
+                        st_cs_pred(outp + (size_t)cc * plane_stride + (size_t)kk * hw, r, kvalid[kk]);
+                    }
                 }
             }
-        }
-        outp += (size_t)kCK * plane_stride;
-        __syncthreads();                               // stage S fully consumed before chunk ch+2 lands in it
-    };
-    static_assert(NCH % 2 == 0, "the stage loop is unrolled by the two pipeline buffers");
+            outp += (size_t)CKc * plane_stride;
+            __syncthreads();                           // stage S fully consumed before chunk ch+2 lands in it
+        };
 #pragma unroll 1
-    for (int ch = 0; ch < NCH; ch += 2) {
-        stage_body(std::integral_constant<int, 0>{}, ch);
-        stage_body(std::integral_constant<int, 1>{}, ch + 1);
-    }
+        for (int ch = 0; ch < NCH; ch += 2) {
+            stage_body(std::integral_constant<int, 0>{}, ch);
+            stage_body(std::integral_constant<int, 1>{}, ch + 1);
+        }
+    };
+    if (cfg == 0) run(std::integral_constant<int, 0>{});
+    else if (cfg == 1) run(std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 2>{});
     if (MODE == MODE_SCORE) {
 #pragma unroll
         for (int kk = 0; kk < kKC; ++kk)
@@ -469,8 +488,12 @@ static int launch_warp_volume_plain(const WarpVolArgs& a, int B, cudaStream_t st
 template <int C, int VS, int MODE>
 static int launch_warp_volume_tma(const WarpVolArgs& a, int B, cudaStream_t st) {
     constexpr size_t smem = sizeof(float) * 2 * VS * kCK * kBox + 2 * sizeof(uint64_t) + VS * 4 * sizeof(int);
-    CUtensorMap tm;
-    if (!make_tmap_4d(&tm, a.feat, a.w, a.h, 1, (long long)B * (VS + 1) * C, kBW, kBH, kCK)) return -100;
+    CUtensorMap tm[kNCfg];
+    for (int j = 0; j < kNCfg; ++j)
+        if (!make_tmap_4d(&tm[j], a.feat, a.w, a.h, 1, (long long)B * (VS + 1) * C, kBW, kBH << j, kCK >> j)) return -100;
+    // test hook (read once per process, like ADAMVS_CONV_CFG): ADAMVS_WARP_CFG=1|2 forces the taller box cuts, 3 the
+    // global-gather path, so that parity tests cover every path on smooth synthetic depth
+    static const int force_cfg = [] { const char* e = getenv("ADAMVS_WARP_CFG"); return (e && *e >= '0' && *e <= '3') ? (*e - '0') : 0; }();
     auto kern = warp_volume_tma_kernel<C, VS, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -478,7 +501,7 @@ static int launch_warp_volume_tma(const WarpVolArgs& a, int B, cudaStream_t st) 
     const long long tiles = (long long)((a.w + kPX - 1) / kPX) * ((a.h + kPY - 1) / kPY);
     if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
     dim3 grid((unsigned)(tiles * nk), B, 1);
-    kern<<<grid, kWvThreads, smem, st>>>(tm, a, nk);
+    kern<<<grid, kWvThreads, smem, st>>>(tm[0], tm[1], tm[2], a, nk, force_cfg);
     ADAMVS_LAUNCH_RESULT();
 }
 

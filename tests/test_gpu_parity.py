@@ -170,7 +170,7 @@ def test_fused_volume_zero_padding_and_behind_camera():
 
 @pytest.mark.parametrize("C,D,h,w,up,prob", [(32, 6, 16, 24, True, "softmax"), (16, 4, 32, 48, True, "exp"),
                                              (8, 3, 64, 96, False, "softmax"), (8, 2, 34, 46, False, "exp")])
-def test_regnet_red_vs_oracle(C, D, h, w, up, prob):
+def test_regnet_red_vs_oracle(C, D, h, w, up, prob, math=None):
     """K3 with the regression folded in: logits, depth and confidence against the oracle's plane loop."""
     ops = _ops()
     from adamvs_b200 import synth
@@ -205,7 +205,8 @@ def test_regnet_red_vs_oracle(C, D, h, w, up, prob):
              "up1_w": ".upconv1.weight", "up1_b": ".upconv1.bias", "out_w": ".upconv2d.weight", "out_b": ".upconv2d.bias"}
     wd = {k: sd[p + v].to(_dev()) for k, v in names.items()}
     hyp = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half_range.to(_dev()))
-    depth, conf, logits = ops.regnet_red(vol.to(_dev()), wd, hyp, up, mode, want_logits=True)
+    kw = {} if math is None else {"math": {"tc": ops.MATH_TC_FP32, "ffma": ops.MATH_FFMA}[math]}
+    depth, conf, logits = ops.regnet_red(vol.to(_dev()), wd, hyp, up, mode, want_logits=True, **kw)
     assert abs_err(logits.cpu(), logits_want) < 1e-4 * max(1.0, float(logits_want.abs().max()))
     assert rel_err(depth.cpu(), depth_want) < DEPTH_RTOL
     assert abs_err(conf.cpu(), conf_want) < PROB_ATOL
@@ -472,6 +473,63 @@ def test_conv_tile_configurations_forced(cfg):
                         "test_regnet_red_vs_oracle or test_regnet_msred_vs_oracle or test_forward_matches_reference_golden"],
                        cwd=root, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+def test_warp_box_cuts_forced(cfg):
+    """The TMA cost-volume kernel re-cuts its stage buffer per block into 4x12-, 2x24- or 1x48-row boxes from the
+    footprint of the tile, and takes the global-gather path beyond that.  Smooth synthetic depth only ever needs the
+    first cut, so the other cuts (ADAMVS_WARP_CFG=1|2) and the gather path (3) are forced in a fresh process and the
+    K1/K2/K5 kernel tests and a whole forward are re-run under them."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ADAMVS_WARP_CFG=cfg)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_pair_score_and_fused_volume_vs_oracle or test_cost_volume_fallback_paths_vs_oracle or "
+                        "test_fused_volume_zero_padding or test_variance_volume or test_forward_matches_reference_golden or "
+                        "test_cost_volume_rough_depth"],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("C,D,h,w,sigma", [(16, 8, 64, 96, 25.0), (8, 4, 96, 128, 8.0), (16, 8, 64, 96, 120.0)])
+def test_cost_volume_rough_depth(C, D, h, w, sigma):
+    """Per-pixel hypotheses around a white-noise depth map (what an untrained stage 1 hands to stage 2): tile
+    footprints spread over tens of source rows, so blocks pick the taller box cuts on their own (and the gather path
+    for the largest sigma).  Same oracle, same tolerance as the smooth case."""
+    ops = _ops()
+    from adamvs_b200 import synth
+    B, V = 2, 5
+    g = torch.Generator().manual_seed(int(sigma) + C)
+    feat = torch.randn(B, V, C, h, w, generator=g)
+    proj = torch.stack([synth.make_cameras(h, w, V - 1)["stage3"], synth.make_cameras(h, w, V - 1, jitter_seed=4)["stage3"]])
+    dv = torch.tensor([[520.0, 680.0], [540.0, 660.0]])
+    wts = torch.rand(B, V - 1, h, w, generator=g) * 0.9 + 0.05
+    relproj, half = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 192,
+                                        [D, D, D], [4.0, 2.0, 1.0])
+    cur = 600 + sigma * torch.randn(B, h, w, generator=g)
+    interval = (float(dv[0, 1]) - float(dv[0, 0])) / 192
+    hyp = ops.Hyp(ops.HYP_PER_PIXEL, cur.to(_dev()), half[1:2])
+    hyps = O.depth_hypotheses(cur, D, 2.0 * interval, [B, h, w])
+    prods = [feat[:, 0].unsqueeze(2) * O.homography_warp(feat[:, v], proj[:, v], proj[:, 0], hyps) for v in range(1, V)]
+    num = sum(p * wts[:, v].unsqueeze(1).unsqueeze(1) for v, p in enumerate(prods))
+    want = num / (1e-5 + wts.sum(1).unsqueeze(1).unsqueeze(1))
+    got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, wts.to(_dev()), ops.EPS_DENOMINATOR, D).cpu()
+    assert float(want.abs().max()) > 0.1
+    assert abs_err(got, want) < 2e-4 * float(want.abs().max())
+    score_want = torch.stack([p.mean(1) for p in prods], 1)
+    score = ops.pair_score(feat.to(_dev()), relproj[0], hyp, D).cpu()
+    assert abs_err(score, score_want) < 2e-4 * float(score_want.abs().max())
+
+
+@pytest.mark.parametrize("C,D,h,w,up,prob", [(32, 6, 16, 24, True, "softmax"), (16, 4, 32, 48, True, "exp"),
+                                             (8, 3, 64, 96, False, "softmax"), (16, 3, 96, 160, True, "softmax")])
+def test_regnet_red_tensor_core_vs_oracle(C, D, h, w, up, prob):
+    """K3 with its stride-1 convolutions on tcgen05 (kind::tf32 with the exact hi/lo operand split, fp32 accumulation
+    in TMEM): the same oracle and the same fp32 tolerances as the FFMA path."""
+    test_regnet_red_vs_oracle(C, D, h, w, up, prob, math="tc")
 
 
 @pytest.mark.parametrize("ca,cb,cout,stride,relu,h,w", [
