@@ -18,6 +18,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("ADAMVS_TC_TRACE"):                # debug build: role timeline of the tcgen05 conv kernel (tools/tc_trace.py)
+    NVCC_FLAGS.append("-DADAMVS_TC_TRACE")
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

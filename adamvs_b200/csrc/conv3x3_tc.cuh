@@ -17,17 +17,22 @@
 // PREC_TF32 drops the A_lo pass (activations rounded to tf32, weights still exact): half the MMA time, reported
 // separately with its own tolerance.
 //
-// Warp-specialised persistent CTA (one per SM, 320 threads), static round-robin tile schedule:
-//   warp 8 lane 0   TMA producer: planar [8 ch][TH+2][40] boxes (halo zero-filled = conv padding) into a slot ring
-//   warps 4-7       converters: planar slot -> hi/lo quad-interleaved operand stage (LDS.32 x4 -> 2 STS.128 per
-//                   position, conflict-free)
-//   warp 9 lane 0   MMA issuer: waits for operand stages, issues MT*9*{hi,lo} MMAs per chunk, tcgen05.commit hands the
+// Warp-specialised persistent CTA (one per SM, 288 threads), static round-robin tile schedule:
+//   warps 4-7       converters: read the tile's input (halo included, out-of-image positions = 0 = conv padding)
+//                   straight from global memory - 8 channels x 5 positions per thread, requested one chunk ahead so
+//                   that the DRAM latency hides behind the MMAs of the previous chunk - split every value and write
+//                   the hi/lo quad-interleaved operand stage (2 + 2 STS.128 per position, conflict-free).  Shared
+//                   memory is the contended resource (the MMAs read ~92 B/clk of operands), so the input makes no
+//                   detour through it: an earlier TMA box ring + LDS transpose cost 2.2x the LSU/TMA traffic
+//   warp 8 lane 0   MMA issuer: waits for operand stages, issues MT*9*{hi,lo} MMAs per chunk, tcgen05.commit hands the
 //                   stage back to the converters and, after a tile's last chunk, the accumulator to the epilogue
 //   warps 0-3       epilogue of the PREVIOUS tile while the MMAs of the current tile run: tcgen05.ld of their TMEM lane
-//                   quarter; the GRU state / gate operands are requested before the accumulators are awaited (one
-//                   round trip per 16 channels instead of one per value), bias + gate non-linearity + GRU blend,
-//                   coalesced row stores
+//                   quarter; the GRU state / gate operands are requested one step ahead (the first step's before the
+//                   accumulator is awaited), bias + gate non-linearity + GRU blend, coalesced row stores
 // Accumulators are double buffered in TMEM (2 x MT x 2*Cout columns).
+// Measured (tools/umma_rate_probe.cu): one M=128 x N<=64 x K=8 kind::tf32 MMA with both operands in shared memory takes
+// 49 clk (operand fetch bound; 64 clk at N=128, 128 at N=256), i.e. 72 x 49 = 3.5 kclk per 8-channel chunk of a
+// 32x15 tile - that is the floor of this formulation.
 #pragma once
 #include "conv3x3.cuh"
 
@@ -35,17 +40,23 @@ namespace adamvs {
 
 enum { PREC_FP32X3 = 0, PREC_TF32 = 1 };
 
+// Debug builds only (ADAMVS_TC_TRACE=1 python adamvs_b200/build.py --force): block 0 of the GRU-1 gate convolution
+// records clock64() stamps of its three roles; tools/tc_trace.py prints the timeline.
+#ifdef ADAMVS_TC_TRACE
+__device__ long long g_tc_trace[3][512][4];
+#define TC_TRACE(role, idx, f) do { if (CA == 8 && CB == 8 && COUT == 16 && PREC == PREC_FP32X3 && blockIdx.x == 0 && (idx) < 512) g_tc_trace[role][idx][f] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, idx, f) do { } while (0)
+#endif
+
 template <int MT_>
 struct TcGeom {
     static constexpr int MT = MT_;                               // M tiles (128 output positions each) per tile
     static constexpr int TW = 32, IPO = TW + 2;                  // operand pitch: tile + left/right halo
     static constexpr int TH = MT * 128 / IPO;                    // 15 rows (MT = 4) | 7 rows (MT = 2)
     static constexpr int IH = TH + 2;
-    static constexpr int BOXW = 40;                              // TMA box: starts 4 columns left of the tile (16-byte rule)
-    static constexpr int BOX_FLOATS = CK * IH * BOXW;
     static constexpr int NPOS = (MT * 128 + 2 * IPO + 2 + 7) / 8 * 8;   // positions any tap of any M row can touch
     static_assert(IH * IPO <= NPOS, "operand plane too small");
-    static_assert((BOX_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -109,42 +120,34 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = NHL * 2 * PLANE_BYTES;      // [hi|lo][2 quads][NPOS][4]
     static constexpr int B_STEP_BYTES = 2 * NB * 16;               // [2 quads][NB rows][4]
     static constexpr int B_BYTES = 9 * NCH * B_STEP_BYTES;
-    static constexpr int SLOT_BYTES = G::BOX_FLOATS * 4;
-    // two operand stages (the converters fill one while the MMAs read the other; a conversion is several times
-    // shorter than a stage's MMAs); everything left goes to the planar TMA ring, whose depth is what hides the
-    // DRAM latency of the boxes (measured with a 2-deep ring: MMAs idle 75 % of the time, profiles/r01q)
-    static constexpr int NA = 2;
-    static constexpr int BUDGET = 227 * 1024 - 512 - B_BYTES - NA * STAGE_BYTES;
-    static constexpr int NSLOT_FIT = BUDGET / SLOT_BYTES;
-    static constexpr int NSLOT = NSLOT_FIT > 6 ? 6 : NSLOT_FIT;    // planar TMA ring
+    static constexpr int BUDGET = 227 * 1024 - 512 - B_BYTES;
+    static constexpr int NA_FIT = BUDGET / STAGE_BYTES;
+    static constexpr int NA = NA_FIT > 4 ? 4 : NA_FIT;             // operand stages
     static constexpr int ACC_COLS = MT * NB;                       // TMEM columns of one accumulator buffer
     static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int NBAR = 2 * NSLOT + 2 * NA + 4;
-    static constexpr size_t SMEM = (size_t)NSLOT * SLOT_BYTES + (size_t)NA * STAGE_BYTES + B_BYTES + 8 * NBAR + 16;
+    static constexpr int NBAR = 2 * NA + 4;
+    static constexpr size_t SMEM = (size_t)NA * STAGE_BYTES + B_BYTES + 8 * NBAR + 16;
     static_assert(CA % CK == 0 && CB % CK == 0, "channel groups must be chunk aligned");
     static_assert(NB % 16 == 0 && NB <= 256, "M = 128 MMAs need N % 16 == 0");
-    static_assert(NSLOT >= 2, "needs a TMA ring of at least two boxes");
+    static_assert(NA >= 2, "needs two operand stages");
     static_assert(2 * ACC_COLS <= 512, "does not fit TMEM");
     static_assert(SMEM <= 227 * 1024, "does not fit shared memory");
     // one CTA per SM is what keeps a 512-column allocation from blocking a co-resident CTA forever
     static_assert(TMEM_COLS <= 256 || SMEM > 114 * 1024, "512-column configurations must be alone on their SM");
 };
 
-constexpr int kTcThreads = 320;     // warps 0-3 epilogue (TMEM lane quarters 0-3), 4-7 converters, 8 TMA producer, 9 MMA issuer
+constexpr int kTcThreads = 288;     // warps 0-3 epilogue (TMEM lane quarters 0-3), 4-7 converters, 8 MMA issuer
 
 template <int CA, int CB, int COUT, int EPI, int MT, int PREC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs a, TileGrid tg) {
+conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
     using C = TcCfg<CA, CB, COUT, MT, PREC>;
     using G = TcGeom<MT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* sSlot = smem_raw;                                         // [NSLOT] planar [8][IH][40]
-    unsigned char* sA = sSlot + C::NSLOT * C::SLOT_BYTES;                    // [NA] operand stages
+    unsigned char* sA = smem_raw;                                            // [NA] operand stages
     unsigned char* sB = sA + C::NA * C::STAGE_BYTES;                         // [9][NCH][2][NB][4]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_BYTES);
-    uint64_t* slot_full = bars;
-    uint64_t* slot_empty = slot_full + C::NSLOT;
-    uint64_t* a_full = slot_empty + C::NSLOT;
+    uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + C::NA;
     uint64_t* d_full = a_empty + C::NA;
     uint64_t* d_empty = d_full + 2;
@@ -157,7 +160,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
         fence_mbar_init();
@@ -186,22 +188,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tiles_per_item = tg.tiles_x * tg.tiles_y;
 
     if (warp == 8) {
-        // ===== TMA producer
-        if (lane == 0) {
-            for (int g = 0; g < total; ++g) {
-                const int slot = g % C::NSLOT;
-                if (g >= C::NSLOT) mbar_wait_bounded(&slot_empty[slot], ((g / C::NSLOT) - 1) & 1);
-                const int ti = g / C::NCH, c = g - ti * C::NCH;
-                const int tile = blockIdx.x + ti * gridDim.x;
-                const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
-                const int ox0 = (r % tg.tiles_x) * G::TW, oy0 = (r / tg.tiles_x) * G::TH;
-                const bool fromA = c * CK < CA;
-                const int plane = fromA ? b * a.planesA + c * CK : b * a.planesB + (c * CK - CA);
-                mbar_expect_tx(&slot_full[slot], C::SLOT_BYTES);
-                tma_load_4d(sSlot + slot * C::SLOT_BYTES, fromA ? &tmA : &tmB, &slot_full[slot], ox0 - 4, oy0 - 1, fromA ? a.k : 0, plane);
-            }
-        }
-    } else if (warp == 9) {
         // ===== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(C::NB);
@@ -212,58 +198,85 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (ti >= 2) mbar_wait_bounded(&d_empty[acc], ((ti >> 1) - 1) & 1);
                 for (int c = 0; c < C::NCH; ++c, ++g) {
                     const int st = g % C::NA;
+                    TC_TRACE(1, g, 0);
                     mbar_wait_bounded(&a_full[st], (g / C::NA) & 1);
                     tc_fence_after();
+                    TC_TRACE(1, g, 1);
                     // descriptors differ only in their 14-bit start-address field (16-byte units; shared memory is
                     // < 256 KB, so adding offsets never carries out of the field)
                     const uint64_t bd0 = umma_desc(b_base + (uint32_t)(c * C::B_STEP_BYTES), C::NB * 16, 128);
-#pragma unroll 1
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t d = tmem + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
-                        const uint64_t ad0 = umma_desc(a_base + (uint32_t)st * C::STAGE_BYTES + (uint32_t)mt * 128 * 16, C::PLANE_BYTES, 128);
+                    // M tile innermost: consecutive MMAs accumulate into different TMEM tiles.  Back-to-back MMAs into
+                    // the SAME accumulator serialise on its read-after-write latency (44-49 clk each for any N <= 64,
+                    // tools/umma_rate_probe.cu); MT independent chains hide it.
+                    const uint64_t ad00 = umma_desc(a_base + (uint32_t)st * C::STAGE_BYTES, C::PLANE_BYTES, 128);
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) {
-                            const uint64_t bd = bd0 + (uint64_t)((t * C::NCH * C::B_STEP_BYTES) >> 4);
+                    for (int t = 0; t < 9; ++t) {
+                        const uint64_t bd = bd0 + (uint64_t)((t * C::NCH * C::B_STEP_BYTES) >> 4);
 #pragma unroll
-                            for (int hl = 0; hl < C::NHL; ++hl) {
-                                const uint64_t ad = ad0 + (uint64_t)((hl * 2 * C::PLANE_BYTES + ((t / 3) * G::IPO + (t % 3)) * 16) >> 4);
-                                umma_tf32(d, ad, bd, idesc, (t | hl) ? 1u : (c ? 1u : 0u));
+                        for (int hl = 0; hl < C::NHL; ++hl) {
+                            const uint64_t ad0 = ad00 + (uint64_t)((hl * 2 * C::PLANE_BYTES + ((t / 3) * G::IPO + (t % 3)) * 16) >> 4);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t d = tmem + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
+                                umma_tf32(d, ad0 + (uint64_t)((mt * 128 * 16) >> 4), bd, idesc, (t | hl) ? 1u : (c ? 1u : 0u));
                             }
                         }
                     }
                     umma_commit(&a_empty[st]);                                 // operand stage free once these MMAs retire
+                    TC_TRACE(1, g, 2);
                 }
                 umma_commit(&d_full[acc]);                                     // accumulator complete
             }
         }
     } else if (warp >= 4) {
-        // ===== converters: planar TMA slot -> hi/lo quad-interleaved operand stage
+        // ===== converters: global memory -> registers (one chunk ahead) -> hi/lo quad-interleaved operand stage
         const int ct = tid - 128;
         constexpr int NPP = G::IH * G::IPO;                                  // positions of one quad plane
         constexpr int NJ = (NPP + 127) / 128;
-        int soff[NJ];                                                        // planar offset of this thread's j-th position
+        int pr[NJ], pc[NJ];                                                  // tile-relative (row, column) of this thread's positions
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const int pos = ct + 128 * j, r = pos / G::IPO, col = pos - r * G::IPO;
-            soff[j] = r * G::BOXW + col + 3;
+            const int pos = ct + 128 * j;
+            pr[j] = pos / G::IPO;
+            pc[j] = pos - pr[j] * G::IPO;
         }
+        const size_t in_plane = (size_t)a.hin * a.win;
+        float pv[NJ][CK];                                                    // the chunk in flight
+        auto fetch = [&](int g) {
+            const int ti = g / C::NCH, c = g - ti * C::NCH;
+            const int tile = blockIdx.x + ti * gridDim.x;
+            const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
+            const int ix0 = (r % tg.tiles_x) * G::TW - 1, iy0 = (r / tg.tiles_x) * G::TH - 1;
+            const bool fromA = c * CK < CA;
+            const float* base = fromA ? a.inA + (size_t)a.k * in_plane + (size_t)b * a.strideA_b + (size_t)(c * CK) * a.strideA_c
+                                      : a.inB + (size_t)b * a.strideB_b + (size_t)(c * CK - CA) * a.strideB_c;
+            const size_t cs = fromA ? (size_t)a.strideA_c : (size_t)a.strideB_c;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int gy = iy0 + pr[j], gx = ix0 + pc[j];
+                const bool in = (j < NJ - 1 || ct + 128 * j < NPP) && gy >= 0 && gy < a.hin && gx >= 0 && gx < a.win;
+                const float* p = base + (in ? (size_t)gy * a.win + gx : 0);
+#pragma unroll
+                for (int e = 0; e < CK; ++e) pv[j][e] = in ? __ldg(p + e * cs) : 0.f;
+            }
+        };
+        if (total > 0) fetch(0);
 #pragma unroll 1
         for (int g = 0; g < total; ++g) {
-            const int slot = g % C::NSLOT, st = g % C::NA;
-            mbar_wait_bounded(&slot_full[slot], (g / C::NSLOT) & 1);
+            const int st = g % C::NA;
+            if (ct == 0) TC_TRACE(0, g, 0);
             if (g >= C::NA) mbar_wait_bounded(&a_empty[st], ((g / C::NA) - 1) & 1);
-            const float* pl = reinterpret_cast<const float*>(sSlot + slot * C::SLOT_BYTES);
+            if (ct == 0) TC_TRACE(0, g, 1);
             unsigned char* stage = sA + (size_t)st * C::STAGE_BYTES;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int j = 0; j < NJ; ++j) {
+                const int pos = ct + 128 * j;
+                if (j == NJ - 1 && pos >= NPP) break;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int pos = ct + 128 * j;
-                    if (j == NJ - 1 && pos >= NPP) break;
-                    const float* src = pl + q * 4 * G::IH * G::BOXW + soff[j];
-                    const float e0 = src[0], e1 = src[G::IH * G::BOXW], e2 = src[2 * G::IH * G::BOXW], e3 = src[3 * G::IH * G::BOXW];
+                for (int q = 0; q < 2; ++q) {
                     float4 h4, l4;
-                    split_tf32(e0, h4.x, l4.x); split_tf32(e1, h4.y, l4.y); split_tf32(e2, h4.z, l4.z); split_tf32(e3, h4.w, l4.w);
+                    split_tf32(pv[j][4 * q + 0], h4.x, l4.x); split_tf32(pv[j][4 * q + 1], h4.y, l4.y);
+                    split_tf32(pv[j][4 * q + 2], h4.z, l4.z); split_tf32(pv[j][4 * q + 3], h4.w, l4.w);
                     float4* dst = reinterpret_cast<float4*>(stage + (size_t)q * C::PLANE_BYTES) + pos;
                     *dst = h4;
                     if (PREC == PREC_FP32X3) *(dst + 2 * G::NPOS) = l4;
@@ -271,7 +284,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             fence_proxy_async();                                               // operand writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&a_full[st]); mbar_arrive(&slot_empty[slot]); }
+            if (lane == 0) mbar_arrive(&a_full[st]);
+            if (ct == 0) TC_TRACE(0, g, 2);
+            if (g + 1 < total) fetch(g + 1);                                   // lands while this thread waits for the next stage
+            if (ct == 0) TC_TRACE(0, g, 3);
         }
     } else {
         // ===== epilogue (warps 0-3 = TMEM lane quarters 0-3): runs one tile behind the MMAs
@@ -349,8 +365,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             };
             float hs0[CG], us0[CG], hs1[CG], us1[CG];
             preload(0, hs0, us0);
+            if (tid == 0) TC_TRACE(2, ti, 0);
             mbar_wait_bounded(&d_full[acc], (ti >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) TC_TRACE(2, ti, 1);
 #pragma unroll
             for (int gi = 0; gi < NG; gi += 2) {
                 if (gi + 1 < NG) preload(gi + 1, hs1, us1);
@@ -363,6 +381,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[acc]);
+            if (tid == 0) TC_TRACE(2, ti, 2);
         }
     }
 
@@ -379,12 +398,9 @@ struct TcLayer {
         return t4 >= 2LL * sm_count() ? 4 : 2;
     }
     static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
+        (void)depthA;
         p.args = a;
         p.cfg = choose_mt(a.hout, a.wout, B);
-        const int IH = (p.cfg == 4 ? TcGeom<4>::IH : TcGeom<2>::IH);
-        if (!make_tmap_4d(&p.tA, a.inA, a.win, a.hin, depthA, (long long)B * a.planesA, 40, IH, CK)) return false;
-        if (CB > 0) { if (!make_tmap_4d(&p.tB, a.inB, a.win, a.hin, 1, (long long)B * a.planesB, 40, IH, CK)) return false; }
-        else p.tB = p.tA;
         return true;
     }
     template <int MT, int PREC>
@@ -405,7 +421,7 @@ struct TcLayer {
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
-        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.tA, p.tB, p.args, p.tg);
+        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.args, p.tg);
         return cudaGetLastError();
     }
     static cudaError_t launch(ConvPlan& p, int B, int prec, cudaStream_t st) {

@@ -320,6 +320,12 @@ extern "C" size_t adamvs_regnet_red_workspace_floats(int B, int C, int D, int h,
     return carve(nullptr, B, C, h, w, out_up).total;
 }
 
+#ifdef ADAMVS_TC_TRACE
+extern "C" int adamvs_tc_trace_read(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, adamvs::g_tc_trace, sizeof(adamvs::g_tc_trace));
+}
+#endif
+
 #define ADAMVS_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 // Default arithmetic of adamvs_regnet_red_f32.  ADAMVS_K3_MATH=ffma|tc|tf32 is a test / measurement hook read once per
@@ -330,6 +336,7 @@ static int default_math() {
         if (e && !strcmp(e, "ffma")) return ADAMVS_MATH_FFMA;
         if (e && !strcmp(e, "tc")) return ADAMVS_MATH_TC_FP32;
         if (e && !strcmp(e, "tf32")) return ADAMVS_MATH_TC_TF32;
+        if (e && !strcmp(e, "auto")) return ADAMVS_MATH_AUTO;
         return ADAMVS_MATH_DEFAULT;
     }();
     return m;
@@ -352,7 +359,8 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
                                         float* depth, float* conf, float* logits_out,
                                         int B, int C, int D, int h, int w, void* stream) {
     ADAMVS_CHECK_ARG(volume && hwts && workspace && depth && conf && hyp_src);
-    ADAMVS_CHECK_ARG(math_mode == ADAMVS_MATH_FFMA || math_mode == ADAMVS_MATH_TC_FP32 || math_mode == ADAMVS_MATH_TC_TF32);
+    ADAMVS_CHECK_ARG(math_mode == ADAMVS_MATH_FFMA || math_mode == ADAMVS_MATH_TC_FP32 || math_mode == ADAMVS_MATH_TC_TF32 ||
+                     math_mode == ADAMVS_MATH_AUTO);
     ADAMVS_CHECK_ARG(B > 0 && B <= 65535 && D >= 2 && h > 0 && w > 0 && (h % 2) == 0 && (w % 2) == 0 && h <= 65535);
     ADAMVS_CHECK_ARG(C == 8 || C == 16 || C == 32);
     ADAMVS_CHECK_ARG(prob_mode == ADAMVS_PROB_SOFTMAX || prob_mode == ADAMVS_PROB_EXP_EPS);
@@ -408,37 +416,45 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
                 && Gates2::plan(p5, a5, B, 1) && Cand2::plan(p6, a6, B, 1);
         tma = ok;
     }
-    // tensor-core layers need the TMA path; planes too small to fill the SMs stay on the split-K FFMA kernels
-    const bool tc = tma && math_mode != ADAMVS_MATH_FFMA;
+    // Which layers run on the tensor cores.  AUTO: measured per layer on B200 (profiles/r01s): the tcgen05 kernels need
+    // ~2 waves of 32x15 tiles to amortise their pipeline, conv1 (memory bound, one chunk per tile at stage 3) and the
+    // GRU-1 candidate conv (N = 16: the MMA is operand-fetch bound at any N <= 64) stay on the FFMA kernels.
     const int prec = math_mode == ADAMVS_MATH_TC_TF32 ? PREC_TF32 : PREC_FP32X3;
+    const long long px = (long long)h * w * B;
+    const bool all_tc = tma && (math_mode == ADAMVS_MATH_TC_FP32 || math_mode == ADAMVS_MATH_TC_TF32);
+    const bool auto_tc = tma && math_mode == ADAMVS_MATH_AUTO;
+    const bool tc1 = all_tc, tc3 = all_tc;
+    const bool tc2 = all_tc || (auto_tc && px >= 400000), tc5 = tc2;
+    const bool tc6 = all_tc || (auto_tc && px >= 1500000);
     ConvPlan q1, q2, q3, q5, q6;
-    if (tc) {
-        bool ok = (C == 8 ? TcConv1<8>::plan(q1, a1, B, D) : C == 16 ? TcConv1<16>::plan(q1, a1, B, D) : TcConv1<32>::plan(q1, a1, B, D));
-        ok = ok && TcGates1::plan(q2, a2, B, 1) && TcCand1::plan(q3, a3, B, 1) && TcGates2::plan(q5, a5, B, 1) && TcCand2::plan(q6, a6, B, 1);
+    {
+        bool ok = true;
+        if (tc1) ok = ok && (C == 8 ? TcConv1<8>::plan(q1, a1, B, D) : C == 16 ? TcConv1<16>::plan(q1, a1, B, D) : TcConv1<32>::plan(q1, a1, B, D));
+        if (tc2) ok = ok && TcGates1::plan(q2, a2, B, 1);
+        if (tc3) ok = ok && TcCand1::plan(q3, a3, B, 1);
+        if (tc5) ok = ok && TcGates2::plan(q5, a5, B, 1);
+        if (tc6) ok = ok && TcCand2::plan(q6, a6, B, 1);
         if (!ok) return ADAMVS_EINVAL;
     }
 
     for (int k = 0; k < D; ++k) {
-        if (tc) {
-            q1.args.k = k;
-            if (C == 8) ADAMVS_TRY(TcConv1<8>::launch(q1, B, prec, st));
-            else if (C == 16) ADAMVS_TRY(TcConv1<16>::launch(q1, B, prec, st));
-            else ADAMVS_TRY(TcConv1<32>::launch(q1, B, prec, st));
-            ADAMVS_TRY(TcGates1::launch(q2, B, prec, st));
-            ADAMVS_TRY(TcCand1::launch(q3, B, prec, st));
+        if (tma) {
+            if (tc1) {
+                q1.args.k = k;
+                if (C == 8) ADAMVS_TRY(TcConv1<8>::launch(q1, B, prec, st));
+                else if (C == 16) ADAMVS_TRY(TcConv1<16>::launch(q1, B, prec, st));
+                else ADAMVS_TRY(TcConv1<32>::launch(q1, B, prec, st));
+            } else {
+                p1.args.k = k;
+                if (C == 8) ADAMVS_TRY(Conv1<8>::launch(p1, B, st));
+                else if (C == 16) ADAMVS_TRY(Conv1<16>::launch(p1, B, st));
+                else ADAMVS_TRY(Conv1<32>::launch(p1, B, st));
+            }
+            if (tc2) ADAMVS_TRY(TcGates1::launch(q2, B, prec, st)); else ADAMVS_TRY(Gates1::launch(p2, B, st));
+            if (tc3) ADAMVS_TRY(TcCand1::launch(q3, B, prec, st)); else ADAMVS_TRY(Cand1::launch(p3, B, st));
             ADAMVS_TRY(Conv2::launch(p4, B, st));
-            ADAMVS_TRY(TcGates2::launch(q5, B, prec, st));
-            ADAMVS_TRY(TcCand2::launch(q6, B, prec, st));
-        } else if (tma) {
-            p1.args.k = k;
-            if (C == 8) ADAMVS_TRY(Conv1<8>::launch(p1, B, st));
-            else if (C == 16) ADAMVS_TRY(Conv1<16>::launch(p1, B, st));
-            else ADAMVS_TRY(Conv1<32>::launch(p1, B, st));
-            ADAMVS_TRY(Gates1::launch(p2, B, st));
-            ADAMVS_TRY(Cand1::launch(p3, B, st));
-            ADAMVS_TRY(Conv2::launch(p4, B, st));
-            ADAMVS_TRY(Gates2::launch(p5, B, st));
-            ADAMVS_TRY(Cand2::launch(p6, B, st));
+            if (tc5) ADAMVS_TRY(TcGates2::launch(q5, B, prec, st)); else ADAMVS_TRY(Gates2::launch(p5, B, st));
+            if (tc6) ADAMVS_TRY(TcCand2::launch(q6, B, prec, st)); else ADAMVS_TRY(Cand2::launch(p6, B, st));
         } else {
             a1.inA = volume + (size_t)k * hw;
             if (C == 8) ADAMVS_TRY(run_conv1<8>(a1, B, st));

@@ -19,7 +19,7 @@ HYP_PLANES, HYP_PER_PIXEL = 0, 1
 EPS_NUMERATOR, EPS_DENOMINATOR = 0, 1
 PROB_SOFTMAX, PROB_EXP_EPS = 0, 1
 INTERVAL_LAST_COLUMN, INTERVAL_FROM_RANGE = 0, 1
-MATH_FFMA, MATH_TC_FP32, MATH_TC_TF32 = 0, 1, 2
+MATH_FFMA, MATH_TC_FP32, MATH_TC_TF32, MATH_AUTO = 0, 1, 2, 3
 
 EXPORTS = (
     "adamvs_abi_version", "adamvs_cascade_prepare", "adamvs_pair_score_f32", "adamvs_resize_bilinear_f32",
@@ -229,7 +229,7 @@ def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob
                workspace: Optional[torch.Tensor] = None, want_logits: bool = False, math: Optional[int] = None):
     """volume [B,C,D,h,w] -> depth, conf [B,Ho,Wo] (+ logits [B,D,Ho,Wo] when asked).
     `weights`: name -> contiguous fp32 CUDA tensor in the reference layouts (see RegnetWeights).
-    `math`: None = the library default, or MATH_FFMA / MATH_TC_FP32 / MATH_TC_TF32 (include/adamvs_b200.h)."""
+    `math`: None = the library default, or MATH_FFMA / MATH_TC_FP32 / MATH_TC_TF32 / MATH_AUTO (include/adamvs_b200.h)."""
     volume = _f32c(volume, "volume")
     B, C, D, h, w = volume.shape
     Ho, Wo = (2 * h, 2 * w) if out_up else (h, w)

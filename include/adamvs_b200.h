@@ -118,11 +118,14 @@ int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_weights* host
  *   TC_FP32  tcgen05.mma kind::tf32 with exact hi/lo operand splits (all four partial products, fp32 accumulation in
  *            TMEM): fp32 accuracy, same tolerance as FFMA.
  *   TC_TF32  activations rounded to tf32 (one pass), weights still split: reported separately with its own tolerance.
+ *   AUTO     per layer, whichever of FFMA / TC_FP32 is faster for the plane size (measured on B200):
+ *            both are fp32-accurate, so the choice does not change the tolerance.
  * Planes whose width is not a multiple of 8 fall back to FFMA in every mode. */
 #define ADAMVS_MATH_FFMA    0
 #define ADAMVS_MATH_TC_FP32 1
 #define ADAMVS_MATH_TC_TF32 2
-#define ADAMVS_MATH_DEFAULT ADAMVS_MATH_FFMA
+#define ADAMVS_MATH_AUTO    3
+#define ADAMVS_MATH_DEFAULT ADAMVS_MATH_AUTO
 
 /* adamvs_regnet_red_f32 with an explicit arithmetic mode (adamvs_regnet_red_f32 uses ADAMVS_MATH_DEFAULT). */
 int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet_weights* host_weights,

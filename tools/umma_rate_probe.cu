@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
 }
 
-template <int N, int SAME_A>
+template <int N, int SAME_A, int ILV>
 __global__ void __launch_bounds__(128) rate(long long* out, int iters) {
     extern __shared__ __align__(128) unsigned char raw[];
     float* sA = reinterpret_cast<float*>(raw);                 // 2 quads x 1200 positions x 4
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) rate(long long* out, int iters) {
                 const uint32_t off = SAME_A ? 0u : (uint32_t)(((t % 9) / 3 * 34 + (t % 3)) * 16 + (t / 9) * 0);
                 const uint64_t ad = make_desc(smem_u32(sA) + off + (uint32_t)((it & 3) * 128 * 16), 1200 * 16, 128);
                 asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                             ::"r"(tmem + (uint32_t)((it & 1) * N)), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                             ::"r"(tmem + (uint32_t)((ILV > 1 ? (t % ILV) : (it & 1)) * N)), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -58,20 +58,20 @@ __global__ void __launch_bounds__(128) rate(long long* out, int iters) {
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int N, int SAME_A>
+template <int N, int SAME_A, int ILV = 1>
 static void run(int blocks) {
     long long* d;
     cudaMalloc(&d, sizeof(long long) * blocks);
     const size_t smem = (2 * 1200 * 4 + 2 * 256 * 4) * 4 + 64;
-    cudaFuncSetAttribute(rate<N, SAME_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(rate<N, SAME_A, ILV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int iters = 2000;
-    rate<N, SAME_A><<<blocks, 128, smem>>>(d, iters);
+    rate<N, SAME_A, ILV><<<blocks, 128, smem>>>(d, iters);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[148] = {0};
     cudaMemcpy(h, d, sizeof(long long) * (blocks < 148 ? blocks : 148), cudaMemcpyDeviceToHost);
     long long mx = 0;
     for (int i = 0; i < blocks && i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
-    printf("N=%3d %s blocks=%3d: %s, %.1f clk per MMA (M=128, K=8)\n", N, SAME_A ? "same A " : "shifted", blocks, cudaGetErrorString(e), (double)mx / (iters * 18.0));
+    printf("N=%3d %s accumulators=%d blocks=%3d: %s, %.1f clk per MMA (M=128, K=8)\n", N, SAME_A ? "same A " : "shifted", ILV, blocks, cudaGetErrorString(e), (double)mx / (iters * 18.0));
     cudaFree(d);
 }
 
@@ -79,5 +79,7 @@ int main() {
     run<16, 0>(1); run<32, 0>(1); run<64, 0>(1); run<128, 0>(1); run<256, 0>(1);
     run<32, 1>(1);
     run<16, 0>(148); run<32, 0>(148); run<64, 0>(148);
+    // consecutive MMAs into different accumulators (no read-after-write chain on D)
+    run<16, 0, 2>(1); run<16, 0, 4>(1); run<32, 0, 2>(1); run<32, 0, 4>(1); run<64, 0, 2>(1); run<64, 0, 4>(1); run<32, 0, 4>(148);
     return 0;
 }
