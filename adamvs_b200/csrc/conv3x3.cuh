@@ -476,6 +476,7 @@ struct ConvPlan {
     int ctas;                // persistent CTAs per output-channel block
     TileGrid tg;
     CUtensorMap tA, tB;
+    CUtensorMap tU, tH;      // tensor-core kernels: GRU epilogue operands (update gate, state)
     ConvArgs args;
 };
 

@@ -1,38 +1,40 @@
 // 3x3 stride-1 convolutions of the recurrent regulariser on the 5th-generation tensor cores: tcgen05.mma kind::tf32,
 // accumulators in TMEM, at fp32 accuracy through an exact hi/lo operand split ("3xTF32", here all four partial products).
 //
-// Implicit GEMM without an im2col copy ("padded linear"): a tile's input (TH+2 rows x 34 columns, halo included) sits
-// in shared memory as [8-channel chunk][hi|lo][channel quad][position][4 channels] - positions enumerate the padded
-// tile row-major with pitch IPO = 34, 16 bytes per position, which is the canonical K-major no-swizzle UMMA operand
-// (core matrix = 8 positions x 16 B, SBO = 128 B, LBO = one quad plane).  Output position m = oy*IPO + ox reads tap
-// (ky,kx) at position m + ky*IPO + kx, so every tap is the SAME operand at a 16-byte-granular start-address offset:
-// per 128 output positions and 8 input channels, 9 taps x {hi, lo} MMAs of M=128 x N x K=8.  Output positions with
-// ox >= 32 are garbage rows of D (6 %) that the epilogue skips.
+// Implicit GEMM without an im2col copy.  A tile's input (4*MT + 2 rows x 32 columns, halo included) sits in shared
+// memory as [8-channel chunk][hi|lo][channel quad][position][4 channels], positions row-major with pitch 32, 16 bytes per
+// position - the canonical K-major no-swizzle UMMA operand (core matrix = 8 positions x 16 B, SBO = 128 B, LBO = one
+// quad plane).  The three ROW taps are operand address offsets: M tile mt, tap row ky reads positions
+// mt*128 + ky*32 + [0,128) - a core-matrix aligned start address.  The three COLUMN taps sit in the MMA's N:
+//     D'[p][kx][co] = sum_ky sum_ci in[p + 32 ky][ci] * W[co][ci][ky][kx]            (N = 3 x 2*Cout)
+//     out[p][co]    = D'[p][0][co] + D'[p+1][1][co] + D'[p+2][2][co]
+// and the shift-and-add over kx is two warp shuffles per value in the epilogue (a warp = one 32-position row of D';
+// its lanes 30, 31 are the halo columns, so a tile is 30 pixels wide).
+// Why: one kind::tf32 MMA of M = 128, K = 8 costs 44-49 clk for ANY N <= ~96 (tools/umma_rate_probe.cu,
+// tools/umma_ts_probe.cu: same with A in TMEM, same with interleaved accumulators) and N/2 clk above that.  With every
+// tap its own MMA (9 taps x {hi,lo} x N = 2*Cout <= 64) the layers ran at 18 x 49 clk per 128 positions and 8 channels,
+// operand-issue bound at 13-34 % tensor-pipe activity (profiles/r01q, r01t).  Folding kx into N issues 3x fewer MMAs
+// (6 per 128 positions and chunk: 49 clk each at N = 48 / 96, 96 clk at N = 192).
 //
 // fp32 accuracy: kind::tf32 reads the top 19 bits of each fp32 word.  Activations and weights are split into
 // hi = rna_tf32(x), lo = rna_tf32(x - hi) (|x - hi - lo| <= 2^-23 |x|); the B operand carries [W_hi rows | W_lo rows]
-// (N = 2*Cout), A_hi and A_lo are multiplied with it in turn and the epilogue adds the two column halves:
-// (A_hi + A_lo)(W_hi + W_lo), fp32 accumulation in TMEM.  An M=128 x K=8 tf32 MMA is bound by the 4 KB shared-memory
-// read of its A tile (32 clk) for every N <= 64, so the doubled N and the lo*lo term are free.
-// PREC_TF32 drops the A_lo pass (activations rounded to tf32, weights still exact): half the MMA time, reported
-// separately with its own tolerance.
+// per kx, A_hi and A_lo are multiplied with it in turn and the epilogue adds the two column halves:
+// (A_hi + A_lo)(W_hi + W_lo), fp32 accumulation in TMEM.  PREC_TF32 drops the A_lo pass (activations rounded to tf32,
+// weights still exact): half the MMAs, reported separately with its own tolerance.
 //
-// Warp-specialised persistent CTA (one per SM, 288 threads), static round-robin tile schedule:
-//   warps 4-7       converters: read the tile's input (halo included, out-of-image positions = 0 = conv padding)
-//                   straight from global memory - 8 channels x 5 positions per thread, requested one chunk ahead so
-//                   that the DRAM latency hides behind the MMAs of the previous chunk - split every value and write
-//                   the hi/lo quad-interleaved operand stage (2 + 2 STS.128 per position, conflict-free).  Shared
-//                   memory is the contended resource (the MMAs read ~92 B/clk of operands), so the input makes no
-//                   detour through it: an earlier TMA box ring + LDS transpose cost 2.2x the LSU/TMA traffic
-//   warp 8 lane 0   MMA issuer: waits for operand stages, issues MT*9*{hi,lo} MMAs per chunk, tcgen05.commit hands the
-//                   stage back to the converters and, after a tile's last chunk, the accumulator to the epilogue
-//   warps 0-3       epilogue of the PREVIOUS tile while the MMAs of the current tile run: tcgen05.ld of their TMEM lane
-//                   quarter; the GRU state / gate operands are requested one step ahead (the first step's before the
-//                   accumulator is awaited), bias + gate non-linearity + GRU blend, coalesced row stores
-// Accumulators are double buffered in TMEM (2 x MT x 2*Cout columns).
-// Measured (tools/umma_rate_probe.cu): one M=128 x N<=64 x K=8 kind::tf32 MMA with both operands in shared memory takes
-// 49 clk (operand fetch bound; 64 clk at N=128, 128 at N=256), i.e. 72 x 49 = 3.5 kclk per 8-channel chunk of a
-// 32x15 tile - that is the floor of this formulation.
+// Warp-specialised persistent CTA (one per SM, 512 threads), static round-robin tile schedule:
+//   warp 8 lane 0   TMA producer: planar [8 ch][4*MT+2][36] boxes (out-of-image elements zero-filled = conv padding)
+//                   into a ring deep enough to cover the DRAM latency; once per tile also the GRU epilogue operands
+//                   (state h for the reset gates, update gate u and h for the candidate blend) of the OUTPUT tile
+//   warps 4-7       converters: planar slot -> split -> hi/lo quad-interleaved operand stage (4 conflict-free LDS.32,
+//                   2 + 2 STS.128 per position; a warp = one row of 32 positions)
+//   warp 9 lane 0   MMA issuer: per chunk 3 (ky) x {hi,lo} x MT MMAs; tcgen05.commit hands the operand stage back to
+//                   the converters and, after a tile's last chunk, the accumulator to the epilogue
+//   warps 0-3,12-15 epilogue of the PREVIOUS tile while the MMAs of the current tile run (accumulators double buffered
+//                   in TMEM, 2 x MT x 3 x 2*Cout columns): tcgen05.ld of their lane quarter (= image row mt*4 + warp%4),
+//                   kx shift-and-add by shuffle, bias + gate non-linearity + GRU blend with operands from the
+//                   producer's ring, all values first and all row stores afterwards; the two warp sets take alternate
+//                   (M tile, 8-channel group) steps
 #pragma once
 #include "conv3x3.cuh"
 
@@ -43,7 +45,7 @@ enum { PREC_FP32X3 = 0, PREC_TF32 = 1 };
 // Debug builds only (ADAMVS_TC_TRACE=1 python adamvs_b200/build.py --force): block 0 of the GRU-1 gate convolution
 // records clock64() stamps of its three roles; tools/tc_trace.py prints the timeline.
 #ifdef ADAMVS_TC_TRACE
-__device__ long long g_tc_trace[3][512][4];
+__device__ long long g_tc_trace[4][512][4];
 #define TC_TRACE(role, idx, f) do { if (CA == 8 && CB == 8 && COUT == 16 && PREC == PREC_FP32X3 && blockIdx.x == 0 && (idx) < 512) g_tc_trace[role][idx][f] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, idx, f) do { } while (0)
@@ -51,12 +53,13 @@ __device__ long long g_tc_trace[3][512][4];
 
 template <int MT_>
 struct TcGeom {
-    static constexpr int MT = MT_;                               // M tiles (128 output positions each) per tile
-    static constexpr int TW = 32, IPO = TW + 2;                  // operand pitch: tile + left/right halo
-    static constexpr int TH = MT * 128 / IPO;                    // 15 rows (MT = 4) | 7 rows (MT = 2)
-    static constexpr int IH = TH + 2;
-    static constexpr int NPOS = (MT * 128 + 2 * IPO + 2 + 7) / 8 * 8;   // positions any tap of any M row can touch
-    static_assert(IH * IPO <= NPOS, "operand plane too small");
+    static constexpr int MT = MT_;                               // M tiles (128 positions = 4 rows x 32) per tile
+    static constexpr int TW = 30, PW = 32;                       // output columns per tile | positions per row (+ 2 halo)
+    static constexpr int TH = 4 * MT, IH = TH + 2;
+    static constexpr int BOXW = 36;                              // TMA box: the start column is rounded down to 4 floats
+    static constexpr int BOX_FLOATS = CK * IH * BOXW;
+    static constexpr int NPOS = IH * PW;                         // positions of one quad plane; the MMAs read exactly these
+    static_assert((BOX_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -82,6 +85,11 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -110,48 +118,78 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
-template <int CA, int CB, int COUT, int MT, int PREC>
+// Activation split for the converters (runs 8 x 10^9 times per depth map): hi = x rounded to tf32 by integer
+// arithmetic (add half an ulp, clear the 13 low bits: 2 instructions; cvt.rna.tf32 compiles to ~5), lo = x - hi (exact in
+// fp32).  lo is handed over unrounded: the tensor core drops its low 13 bits, an error <= 2^-21 |x|.
+__device__ __forceinline__ void split_fast(float v, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    lo = v - hi;
+}
+
+template <int CA, int CB, int COUT, int MT, int PREC, int EPI>
 struct TcCfg {
     using G = TcGeom<MT>;
-    static constexpr int CIN = CA + CB, NCH = CIN / CK;           // 8-channel chunks = K steps per tap
-    static constexpr int NB = 2 * COUT;                            // MMA N: [W_hi rows | W_lo rows]
+    static constexpr int CIN = CA + CB, NCH = CIN / CK;           // 8-channel chunks = K steps per tap row
+    static constexpr int NB = 2 * COUT;                            // [W_hi rows | W_lo rows] of one kx
+    static constexpr int N3 = 3 * NB;                              // MMA N: kx-major
     static constexpr int NHL = PREC == PREC_FP32X3 ? 2 : 1;        // operand passes per stage (hi, lo)
     static constexpr int PLANE_BYTES = G::NPOS * 16;               // one channel quad of one pass
     static constexpr int STAGE_BYTES = NHL * 2 * PLANE_BYTES;      // [hi|lo][2 quads][NPOS][4]
-    static constexpr int B_STEP_BYTES = 2 * NB * 16;               // [2 quads][NB rows][4]
-    static constexpr int B_BYTES = 9 * NCH * B_STEP_BYTES;
-    static constexpr int BUDGET = 227 * 1024 - 512 - B_BYTES;
-    static constexpr int NA_FIT = BUDGET / STAGE_BYTES;
-    static constexpr int NA = NA_FIT > 4 ? 4 : NA_FIT;             // operand stages
-    static constexpr int ACC_COLS = MT * NB;                       // TMEM columns of one accumulator buffer
+    static constexpr int B_STEP_BYTES = 2 * N3 * 16;               // [2 quads][N3 rows][4] of one (ky, chunk)
+    static constexpr int B_BYTES = 3 * NCH * B_STEP_BYTES;
+    static constexpr int SLOT_BYTES = G::BOX_FLOATS * 4;
+    static constexpr int NA = 3;                                   // operand stages
+    // GRU epilogue operands (h for the reset gates; u and h for the candidate blend) travel like the input: the producer
+    // streams [channels][4*MT rows][32] boxes of the output tile into a ring EPI_R tiles deep
+    static constexpr int NGW = MT * (COUT / 8) / 2;                // epilogue steps per warp and tile
+    static constexpr int EPI_CH = EPI == EPI_GATES ? COUT / 2 : (EPI == EPI_CAND ? 2 * COUT : 0);
+    static constexpr int EPI_PLANE = G::TH * 32;                   // floats per channel of a box
+    static constexpr int EPI_TILE_BYTES = EPI_CH * EPI_PLANE * 4;
+    static constexpr int BUDGET0 = 227 * 1024 - 1024 - B_BYTES - NA * STAGE_BYTES;
+    static constexpr int EPI_R = EPI_CH == 0 ? 0 : ((BUDGET0 - 3 * EPI_TILE_BYTES) / SLOT_BYTES >= 4 ? 3 : 2);
+    static constexpr int EPI_BYTES = EPI_R * EPI_TILE_BYTES;
+    static constexpr int BUDGET = BUDGET0 - EPI_BYTES;
+    static constexpr int NSLOT_FIT = BUDGET / SLOT_BYTES;
+    static constexpr int NSLOT = NSLOT_FIT > 6 ? 6 : NSLOT_FIT;    // planar TMA ring
+    static constexpr int ACC_COLS = MT * N3;                       // TMEM columns of one accumulator buffer
     static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int NBAR = 2 * NA + 4;
-    static constexpr size_t SMEM = (size_t)NA * STAGE_BYTES + B_BYTES + 8 * NBAR + 16;
+    static constexpr int NBAR = 2 * NSLOT + 2 * NA + 4 + 2 * 3;
+    static constexpr size_t SMEM_USED = (size_t)NSLOT * SLOT_BYTES + (size_t)NA * STAGE_BYTES + B_BYTES + EPI_BYTES + 8 * NBAR + 16;
+    // every configuration allocates more than half of TMEM: ask for more than half of the shared memory too, so that a
+    // second CTA can never become resident on the SM and spin forever in tcgen05.alloc
+    static constexpr size_t SMEM = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
     static_assert(CA % CK == 0 && CB % CK == 0, "channel groups must be chunk aligned");
-    static_assert(NB % 16 == 0 && NB <= 256, "M = 128 MMAs need N % 16 == 0");
-    static_assert(NA >= 2, "needs two operand stages");
+    static_assert(N3 % 16 == 0 && N3 <= 256, "M = 128 MMAs need N % 16 == 0, N <= 256");
+    static_assert(NSLOT >= 2, "needs a TMA ring of at least two boxes");
     static_assert(2 * ACC_COLS <= 512, "does not fit TMEM");
     static_assert(SMEM <= 227 * 1024, "does not fit shared memory");
-    // one CTA per SM is what keeps a 512-column allocation from blocking a co-resident CTA forever
-    static_assert(TMEM_COLS <= 256 || SMEM > 114 * 1024, "512-column configurations must be alone on their SM");
 };
 
-constexpr int kTcThreads = 288;     // warps 0-3 epilogue (TMEM lane quarters 0-3), 4-7 converters, 8 MMA issuer
+// warps 0-3 and 12-15: epilogue (TMEM lane quarter = warp % 4; the two sets take alternate steps), 4-7 converters,
+// 8 TMA producer, 9 MMA issuer, 10-11 idle
+constexpr int kTcThreads = 512;
 
 template <int CA, int CB, int COUT, int EPI, int MT, int PREC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
-    using C = TcCfg<CA, CB, COUT, MT, PREC>;
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH, ConvArgs a, TileGrid tg) {
+    using C = TcCfg<CA, CB, COUT, MT, PREC, EPI>;
     using G = TcGeom<MT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* sA = smem_raw;                                            // [NA] operand stages
-    unsigned char* sB = sA + C::NA * C::STAGE_BYTES;                         // [9][NCH][2][NB][4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_BYTES);
-    uint64_t* a_full = bars;
+    unsigned char* sSlot = smem_raw;                                         // [NSLOT] planar [8][IH][36]
+    unsigned char* sA = sSlot + C::NSLOT * C::SLOT_BYTES;                    // [NA] operand stages
+    unsigned char* sB = sA + C::NA * C::STAGE_BYTES;                         // [3 ky][NCH][2 quads][N3][4]
+    float* sEpi = reinterpret_cast<float*>(sB + C::B_BYTES);                 // [EPI_R][u channels | h channels][TH][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_BYTES + C::EPI_BYTES);
+    uint64_t* slot_full = bars;
+    uint64_t* slot_empty = slot_full + C::NSLOT;
+    uint64_t* a_full = slot_empty + C::NSLOT;
     uint64_t* a_empty = a_full + C::NA;
     uint64_t* d_full = a_empty + C::NA;
     uint64_t* d_empty = d_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    uint64_t* e_full = d_empty + 2;
+    uint64_t* e_empty = e_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_empty + 3);
     __shared__ float sBias[COUT];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -160,23 +198,28 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
+        for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 8); }
         fence_mbar_init();
     }
     if (tid < COUT) sBias[tid] = (EPI == EPI_RELU || a.bias == nullptr) ? 0.f : __ldg(a.bias + tid);
-    // resident weights: [ci][tap][co] -> B operand [tap][chunk][quad][W_hi co | W_lo co][4 ci], split once per CTA
+    // resident weights: [ci][tap][co] -> B operand [ky][chunk][quad][kx: W_hi co | W_lo co][4 ci], split once per CTA
     for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += kTcThreads) {
-        const int j = i & 3, n = (i >> 2) % COUT, kq = (i / (4 * COUT)) & 1, s = (i / (8 * COUT)) % C::NCH, t = i / (8 * COUT * C::NCH);
-        const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + t) * COUT + n);
+        int r = i;
+        const int j = r & 3; r >>= 2;
+        const int n = r % COUT; r /= COUT;
+        const int kx = r % 3; r /= 3;
+        const int kq = r & 1; r >>= 1;
+        const int s = r % C::NCH, ky = r / C::NCH;
+        const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + ky * 3 + kx) * COUT + n);
         float hi, lo;
         split_tf32(v, hi, lo);
-        float* dst = reinterpret_cast<float*>(sB + (size_t)(t * C::NCH + s) * C::B_STEP_BYTES + kq * C::NB * 16);
+        float* dst = reinterpret_cast<float*>(sB + (size_t)(ky * C::NCH + s) * C::B_STEP_BYTES + kq * C::N3 * 16) + kx * C::NB * 4;
         dst[n * 4 + j] = hi;
         dst[(COUT + n) * 4 + j] = lo;
     }
-    // positions past the tile are read only by garbage rows of D; give them finite values once
-    for (int i = tid; i < C::NA * C::STAGE_BYTES / 16; i += kTcThreads) reinterpret_cast<float4*>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -188,9 +231,37 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
     const int tiles_per_item = tg.tiles_x * tg.tiles_y;
 
     if (warp == 8) {
+        // ===== TMA producer
+        if (lane == 0) {
+            for (int g = 0; g < total; ++g) {
+                const int slot = g % C::NSLOT;
+                if (g >= C::NSLOT) mbar_wait_bounded(&slot_empty[slot], ((g / C::NSLOT) - 1) & 1);
+                const int ti = g / C::NCH, c = g - ti * C::NCH;
+                const int tile = blockIdx.x + ti * gridDim.x;
+                const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
+                const int ox0 = (r % tg.tiles_x) * G::TW, oy0 = (r / tg.tiles_x) * G::TH;
+                if (C::EPI_R > 0 && c == 0) {                                  // this tile's epilogue operands
+                    const int es = ti % (C::EPI_R > 0 ? C::EPI_R : 1);
+                    if (ti >= C::EPI_R) mbar_wait_bounded(&e_empty[es], ((ti / (C::EPI_R > 0 ? C::EPI_R : 1)) - 1) & 1);
+                    float* dstE = sEpi + (size_t)es * (C::EPI_TILE_BYTES / 4);
+                    mbar_expect_tx(&e_full[es], C::EPI_TILE_BYTES);
+                    if (EPI == EPI_GATES) {
+                        tma_load_4d(dstE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * (COUT / 2));
+                    } else {
+                        tma_load_4d(dstE, &tmU, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
+                        tma_load_4d(dstE + COUT * C::EPI_PLANE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
+                    }
+                }
+                const bool fromA = c * CK < CA;
+                const int plane = fromA ? b * a.planesA + c * CK : b * a.planesB + (c * CK - CA);
+                mbar_expect_tx(&slot_full[slot], C::SLOT_BYTES);
+                tma_load_4d(sSlot + slot * C::SLOT_BYTES, fromA ? &tmA : &tmB, &slot_full[slot], (ox0 - 1) & ~3, oy0 - 1, fromA ? a.k : 0, plane);
+            }
+        }
+    } else if (warp == 9) {
         // ===== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(C::NB);
+            const uint32_t idesc = umma_idesc_tf32(C::N3);
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             int g = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
@@ -204,21 +275,18 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
                     TC_TRACE(1, g, 1);
                     // descriptors differ only in their 14-bit start-address field (16-byte units; shared memory is
                     // < 256 KB, so adding offsets never carries out of the field)
-                    const uint64_t bd0 = umma_desc(b_base + (uint32_t)(c * C::B_STEP_BYTES), C::NB * 16, 128);
-                    // M tile innermost: consecutive MMAs accumulate into different TMEM tiles.  Back-to-back MMAs into
-                    // the SAME accumulator serialise on its read-after-write latency (44-49 clk each for any N <= 64,
-                    // tools/umma_rate_probe.cu); MT independent chains hide it.
                     const uint64_t ad00 = umma_desc(a_base + (uint32_t)st * C::STAGE_BYTES, C::PLANE_BYTES, 128);
+                    const uint64_t bd00 = umma_desc(b_base + (uint32_t)(c * C::B_STEP_BYTES), C::N3 * 16, 128);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const uint64_t bd = bd0 + (uint64_t)((t * C::NCH * C::B_STEP_BYTES) >> 4);
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint64_t bd = bd00 + (uint64_t)((ky * C::NCH * C::B_STEP_BYTES) >> 4);
 #pragma unroll
                         for (int hl = 0; hl < C::NHL; ++hl) {
-                            const uint64_t ad0 = ad00 + (uint64_t)((hl * 2 * C::PLANE_BYTES + ((t / 3) * G::IPO + (t % 3)) * 16) >> 4);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
-                                const uint32_t d = tmem + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
-                                umma_tf32(d, ad0 + (uint64_t)((mt * 128 * 16) >> 4), bd, idesc, (t | hl) ? 1u : (c ? 1u : 0u));
+                                const uint32_t d = tmem + (uint32_t)(acc * C::ACC_COLS + mt * C::N3);
+                                const uint64_t ad = ad00 + (uint64_t)((hl * 2 * C::PLANE_BYTES + (mt * 128 + ky * G::PW) * 16) >> 4);
+                                umma_tf32(d, ad, bd, idesc, (ky | hl) ? 1u : (c ? 1u : 0u));
                             }
                         }
                     }
@@ -228,55 +296,43 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
                 umma_commit(&d_full[acc]);                                     // accumulator complete
             }
         }
-    } else if (warp >= 4) {
-        // ===== converters: global memory -> registers (one chunk ahead) -> hi/lo quad-interleaved operand stage
-        const int ct = tid - 128;
-        constexpr int NPP = G::IH * G::IPO;                                  // positions of one quad plane
-        constexpr int NJ = (NPP + 127) / 128;
-        int pr[NJ], pc[NJ];                                                  // tile-relative (row, column) of this thread's positions
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int pos = ct + 128 * j;
-            pr[j] = pos / G::IPO;
-            pc[j] = pos - pr[j] * G::IPO;
-        }
-        const size_t in_plane = (size_t)a.hin * a.win;
-        float pv[NJ][CK];                                                    // the chunk in flight
-        auto fetch = [&](int g) {
-            const int ti = g / C::NCH, c = g - ti * C::NCH;
-            const int tile = blockIdx.x + ti * gridDim.x;
-            const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
-            const int ix0 = (r % tg.tiles_x) * G::TW - 1, iy0 = (r / tg.tiles_x) * G::TH - 1;
-            const bool fromA = c * CK < CA;
-            const float* base = fromA ? a.inA + (size_t)a.k * in_plane + (size_t)b * a.strideA_b + (size_t)(c * CK) * a.strideA_c
-                                      : a.inB + (size_t)b * a.strideB_b + (size_t)(c * CK - CA) * a.strideB_c;
-            const size_t cs = fromA ? (size_t)a.strideA_c : (size_t)a.strideB_c;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int gy = iy0 + pr[j], gx = ix0 + pc[j];
-                const bool in = (j < NJ - 1 || ct + 128 * j < NPP) && gy >= 0 && gy < a.hin && gx >= 0 && gx < a.win;
-                const float* p = base + (in ? (size_t)gy * a.win + gx : 0);
-#pragma unroll
-                for (int e = 0; e < CK; ++e) pv[j][e] = in ? __ldg(p + e * cs) : 0.f;
-            }
-        };
-        if (total > 0) fetch(0);
+    } else if (warp >= 4 && warp < 8) {
+        // ===== converters: planar TMA slot -> hi/lo quad-interleaved operand stage; warp cw converts rows cw, cw+4, ...
+        const int cw = warp - 4;
+        constexpr int NJ = (G::IH + 3) / 4;
 #pragma unroll 1
         for (int g = 0; g < total; ++g) {
-            const int st = g % C::NA;
-            if (ct == 0) TC_TRACE(0, g, 0);
+            const int slot = g % C::NSLOT, st = g % C::NA;
+            const int ti = g / C::NCH;
+            const int tile = blockIdx.x + ti * gridDim.x;
+            const int rr = tile % tiles_per_item;
+            const int ox0 = (rr % tg.tiles_x) * G::TW;
+            const int off = (ox0 - 1) - ((ox0 - 1) & ~3);                     // column of position 0 inside the box
+            if (cw == 0 && lane == 0) TC_TRACE(0, g, 0);
+            mbar_wait_bounded(&slot_full[slot], (g / C::NSLOT) & 1);
             if (g >= C::NA) mbar_wait_bounded(&a_empty[st], ((g / C::NA) - 1) & 1);
-            if (ct == 0) TC_TRACE(0, g, 1);
+            if (cw == 0 && lane == 0) TC_TRACE(0, g, 1);
+            const float* pl = reinterpret_cast<const float*>(sSlot + slot * C::SLOT_BYTES) + off + lane;
             unsigned char* stage = sA + (size_t)st * C::STAGE_BYTES;
+            // all loads first (the compiler cannot move a shared-memory load above an earlier shared-memory store)
+            float e[NJ][CK];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                const int pos = ct + 128 * j;
-                if (j == NJ - 1 && pos >= NPP) break;
+                const int r = cw + 4 * j;
+                const bool on = j < NJ - 1 || r < G::IH;                       // warp-uniform
+#pragma unroll
+                for (int ch = 0; ch < CK; ++ch) e[j][ch] = on ? pl[(ch * G::IH + (on ? r : 0)) * G::BOXW] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int r = cw + 4 * j;
+                if (j == NJ - 1 && r >= G::IH) break;                          // warp-uniform
+                const int pos = r * G::PW + lane;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     float4 h4, l4;
-                    split_tf32(pv[j][4 * q + 0], h4.x, l4.x); split_tf32(pv[j][4 * q + 1], h4.y, l4.y);
-                    split_tf32(pv[j][4 * q + 2], h4.z, l4.z); split_tf32(pv[j][4 * q + 3], h4.w, l4.w);
+                    split_fast(e[j][4 * q + 0], h4.x, l4.x); split_fast(e[j][4 * q + 1], h4.y, l4.y);
+                    split_fast(e[j][4 * q + 2], h4.z, l4.z); split_fast(e[j][4 * q + 3], h4.w, l4.w);
                     float4* dst = reinterpret_cast<float4*>(stage + (size_t)q * C::PLANE_BYTES) + pos;
                     *dst = h4;
                     if (PREC == PREC_FP32X3) *(dst + 2 * G::NPOS) = l4;
@@ -284,15 +340,16 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
             }
             fence_proxy_async();                                               // operand writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[st]);
-            if (ct == 0) TC_TRACE(0, g, 2);
-            if (g + 1 < total) fetch(g + 1);                                   // lands while this thread waits for the next stage
-            if (ct == 0) TC_TRACE(0, g, 3);
+            if (lane == 0) { mbar_arrive(&a_full[st]); mbar_arrive(&slot_empty[slot]); }
+            if (cw == 0 && lane == 0) TC_TRACE(0, g, 2);
         }
-    } else {
-        // ===== epilogue (warps 0-3 = TMEM lane quarters 0-3): runs one tile behind the MMAs
+    } else if (warp < 4 || warp >= 12) {
+        // ===== epilogue (TMEM lane quarter = warp % 4 = image row mt*4 + quarter): runs one tile behind the MMAs.  One warp
+        // per scheduler is latency bound (TMEM load -> shuffles -> MUFU -> stores: ~4.4 clk per instruction measured),
+        // so two warps per quarter take alternate (M tile, channel group) steps.
+        const int quarter = warp & 3, eset = warp >= 12 ? 1 : 0;
         const size_t plane = (size_t)a.hout * a.wout;
-        constexpr int CG = COUT < 16 ? COUT : 16;                            // output channels per TMEM load pair
+        constexpr int CG = 8;                                                // output channels per step
         constexpr int NCG = COUT / CG, NG = MT * NCG;                        // (M tile, channel group) steps per tile
         constexpr int HC = COUT / 2;
 #pragma unroll 1
@@ -300,87 +357,79 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
             const int acc = ti & 1;
             const int tile = blockIdx.x + ti * gridDim.x;
             const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
-            const int ox0 = (rr % tg.tiles_x) * G::TW, oy0 = (rr / tg.tiles_x) * G::TH;
-            auto geom = [&](int mt, bool& valid, size_t& pix) {
-                const int m = mt * 128 + warp * 32 + lane;
-                const int ry = m / G::IPO, rx = m - ry * G::IPO;
-                const int oy = oy0 + ry, ox = ox0 + rx;
-                valid = ry < G::TH && rx < G::TW && oy < a.hout && ox < a.wout;
-                pix = valid ? (size_t)oy * a.wout + ox : 0;
-            };
-            // GRU state / gate operands of step gi: requested one step ahead (the first step's before the accumulator
-            // is awaited), so their DRAM latency overlaps the MMAs / the previous step instead of stalling every step
-            auto preload = [&](int gi, float (&hs)[CG], float (&us)[CG]) {
-                if (EPI != EPI_GATES && EPI != EPI_CAND) return;
+            const int ox = (rr % tg.tiles_x) * G::TW + lane, oy0 = (rr / tg.tiles_x) * G::TH + quarter;
+            auto process = [&](int sI) {
+                const int gi = eset + 2 * sI;
                 const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
-                bool valid; size_t pix;
-                geom(mt, valid, pix);
-                if (EPI == EPI_GATES) {
-#pragma unroll
-                    for (int c = 0; c < CG; ++c)
-                        hs[c] = (valid && c0 + c < HC) ? __ldg(a.hstate + ((size_t)b * HC + c0 + c) * plane + pix) : 0.f;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CG; ++c) {
-                        const size_t o = ((size_t)b * COUT + c0 + c) * plane + pix;
-                        us[c] = valid ? __ldg(a.ugate + o) : 0.f;
-                        hs[c] = valid ? a.hstate[o] : 0.f;
-                    }
-                }
-            };
-            auto process = [&](int gi, const float (&hs)[CG], const float (&us)[CG]) {
-                const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
-                bool valid; size_t pix;
-                geom(mt, valid, pix);
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * C::NB);
-                uint32_t rh[16], rl[16];
+                // GRU operands of this pixel: box row 4*mt + quarter, column (ox0 - aligned box start) + lane
+                const float* opnd = sEpi + (size_t)(ti % (C::EPI_R > 0 ? C::EPI_R : 1)) * (C::EPI_TILE_BYTES / 4)
+                                  + (4 * mt + quarter) * 32 + (ox - lane - ((ox - lane) & ~3)) + lane;
+                const int oy = oy0 + 4 * mt;
+                const bool valid = lane < G::TW && oy < a.hout && ox < a.wout;
+                const size_t pix = valid ? (size_t)oy * a.wout + ox : 0;
+                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * C::N3);
                 float v[CG];
-                if (COUT >= 16) {
-                    tmem_ld16_issue(taddr + c0, rh);                           // columns of A x W_hi
-                    tmem_ld16_issue(taddr + COUT + c0, rl);                    // columns of A x W_lo
-                } else {                                                       // COUT == 8: both halves in one 16-column load
-                    tmem_ld16_issue(taddr, rh);
+                // all six loads in flight before the one wait (kx x {A W_hi, A W_lo} columns of this channel group)
+                uint32_t rh[3][8], rl[3][8];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    tmem_ld8_issue(taddr + kx * C::NB + c0, rh[kx]);
+                    tmem_ld8_issue(taddr + kx * C::NB + COUT + c0, rl[kx]);
                 }
                 tmem_ld_wait();
+                if (tid == 0 && gi == 0) TC_TRACE(3, ti, 0);
 #pragma unroll
-                for (int c = 0; c < CG; ++c)
-                    v[c] = COUT >= 16 ? __uint_as_float(rh[c]) + __uint_as_float(rl[c]) : __uint_as_float(rh[c]) + __uint_as_float(rh[(COUT + c) & 15]);
+                for (int c = 0; c < CG; ++c) {
+                    // out[p] = D'[p][0] + D'[p+1][1] + D'[p+2][2]: the neighbours' partial sums come by shuffle
+                    v[c] = __uint_as_float(rh[0][c]) + __uint_as_float(rl[0][c]);
+                    v[c] += __shfl_down_sync(0xffffffffu, __uint_as_float(rh[1][c]) + __uint_as_float(rl[1][c]), 1);
+                    v[c] += __shfl_down_sync(0xffffffffu, __uint_as_float(rh[2][c]) + __uint_as_float(rl[2][c]), 2);
+                }
+                if (tid == 0 && gi == 0) TC_TRACE(3, ti, 1);
                 if (!valid) return;
+                // All values first, all stores afterwards: the operands below come from (generic-address) shared memory,
+                // and the compiler will not move such a load above an earlier global store - with load, MUFU and store
+                // interleaved per channel the eight ~180-clk dependency chains ran one after the other (profiles/r02e).
+                float res[CG];
 #pragma unroll
                 for (int c = 0; c < CG; ++c) {
                     const int co = c0 + c;
                     if (EPI == EPI_GATES) {
                         const float s = sigmoid_f(v[c] + sBias[co]);
-                        if (co < HC) a.out0[((size_t)b * HC + co) * plane + pix] = s * hs[c];      // reset gate -> r*h
-                        else a.out1[((size_t)b * HC + (co - HC)) * plane + pix] = s;
+                        res[c] = co < HC ? s * opnd[(co < HC ? co : 0) * C::EPI_PLANE] : s;      // reset gate -> r*h | update gate
                     } else if (EPI == EPI_CAND) {
-                        a.out0[((size_t)b * COUT + co) * plane + pix] = us[c] * hs[c] + (1.f - us[c]) * tanh_f(v[c] + sBias[co]);
+                        const float u = opnd[co * C::EPI_PLANE], hv = opnd[(COUT + co) * C::EPI_PLANE];
+                        res[c] = u * hv + (1.f - u) * tanh_f(v[c] + sBias[co]);
                     } else if (EPI == EPI_RELU) {
-                        a.out0[((size_t)b * COUT + co) * plane + pix] = fmaxf(v[c], 0.f);
+                        res[c] = fmaxf(v[c], 0.f);
                     } else {                                                   // EPI_BIAS
                         const float y = v[c] + sBias[co];
-                        a.out0[((size_t)b * COUT + co) * plane + pix] = a.relu ? fmaxf(y, 0.f) : y;
+                        res[c] = a.relu ? fmaxf(y, 0.f) : y;
                     }
                 }
+                {
+                    float* dst;
+                    if (EPI == EPI_GATES) dst = c0 < HC ? a.out0 + ((size_t)b * HC + c0) * plane + pix : a.out1 + ((size_t)b * HC + (c0 - HC)) * plane + pix;
+                    else dst = a.out0 + ((size_t)b * COUT + c0) * plane + pix;
+#pragma unroll
+                    for (int c = 0; c < CG; ++c) dst[(size_t)c * plane] = res[c];
+                }
+                if (tid == 0 && gi == 0) TC_TRACE(3, ti, 2);
             };
-            float hs0[CG], us0[CG], hs1[CG], us1[CG];
-            preload(0, hs0, us0);
+            static_assert(NG % 2 == 0 && C::NGW == NG / 2, "the two epilogue warp sets split the steps evenly");
             if (tid == 0) TC_TRACE(2, ti, 0);
             mbar_wait_bounded(&d_full[acc], (ti >> 1) & 1);
             tc_fence_after();
+            if (C::EPI_R > 0) mbar_wait_bounded(&e_full[ti % (C::EPI_R > 0 ? C::EPI_R : 1)], (ti / (C::EPI_R > 0 ? C::EPI_R : 1)) & 1);
             if (tid == 0) TC_TRACE(2, ti, 1);
 #pragma unroll
-            for (int gi = 0; gi < NG; gi += 2) {
-                if (gi + 1 < NG) preload(gi + 1, hs1, us1);
-                process(gi, hs0, us0);
-                if (gi + 1 < NG) {
-                    if (gi + 2 < NG) preload(gi + 2, hs0, us0);
-                    process(gi + 1, hs1, us1);
-                }
-            }
+            for (int sI = 0; sI < C::NGW; ++sI) process(sI);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[acc]);
+            if (lane == 0) {
+                mbar_arrive(&d_empty[acc]);
+                if (C::EPI_R > 0) mbar_arrive(&e_empty[ti % (C::EPI_R > 0 ? C::EPI_R : 1)]);
+            }
             if (tid == 0) TC_TRACE(2, ti, 2);
         }
     }
@@ -392,20 +441,27 @@ conv3x3_tc_kernel(ConvArgs a, TileGrid tg) {
 
 template <int CA, int CB, int COUT, int EPI>
 struct TcLayer {
-    // plane sizes below ~2 waves of 15-row tiles use 7-row tiles (MT = 2)
-    static int choose_mt(int hout, int wout, int B) {
-        const long long t4 = (long long)((wout + 31) / 32) * ((hout + TcGeom<4>::TH - 1) / TcGeom<4>::TH) * B;
-        return t4 >= 2LL * sm_count() ? 4 : 2;
-    }
+    // M tiles per tile: as many as the double-buffered accumulator (2 x MT x 6*Cout columns) fits into TMEM
+    static constexpr int MT = COUT <= 8 ? (EPI == EPI_CAND ? 2 : 4) : (COUT <= 16 ? 2 : 1);
+    using G = TcGeom<MT>;
     static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
-        (void)depthA;
         p.args = a;
-        p.cfg = choose_mt(a.hout, a.wout, B);
+        p.cfg = MT;
+        if (!make_tmap_4d(&p.tA, a.inA, a.win, a.hin, depthA, (long long)B * a.planesA, G::BOXW, G::IH, CK)) return false;
+        if (CB > 0) { if (!make_tmap_4d(&p.tB, a.inB, a.win, a.hin, 1, (long long)B * a.planesB, G::BOXW, G::IH, CK)) return false; }
+        else p.tB = p.tA;
+        p.tU = p.tA; p.tH = p.tA;
+        if (EPI == EPI_GATES) {
+            if (!make_tmap_4d(&p.tH, a.hstate, a.wout, a.hout, 1, (long long)B * (COUT / 2), 32, G::TH, COUT / 2)) return false;
+        } else if (EPI == EPI_CAND) {
+            if (!make_tmap_4d(&p.tU, a.ugate, a.wout, a.hout, 1, (long long)B * COUT, 32, G::TH, COUT)) return false;
+            if (!make_tmap_4d(&p.tH, a.hstate, a.wout, a.hout, 1, (long long)B * COUT, 32, G::TH, COUT)) return false;
+        }
         return true;
     }
-    template <int MT, int PREC>
-    static cudaError_t launch_cfg(ConvPlan& p, int B, cudaStream_t st) {
-        using C = TcCfg<CA, CB, COUT, MT, PREC>;
+    template <int PREC>
+    static cudaError_t launch_prec(ConvPlan& p, int B, cudaStream_t st) {
+        using C = TcCfg<CA, CB, COUT, MT, PREC, EPI>;
         auto kern = conv3x3_tc_kernel<CA, CB, COUT, EPI, MT, PREC>;
         static bool ready[64] = {false};
         int dev = 0;
@@ -416,17 +472,16 @@ struct TcLayer {
             if (e != cudaSuccess) return e;
             ready[dev] = true;
         }
-        p.tg.tiles_x = (p.args.wout + TcGeom<MT>::TW - 1) / TcGeom<MT>::TW;
-        p.tg.tiles_y = (p.args.hout + TcGeom<MT>::TH - 1) / TcGeom<MT>::TH;
+        p.tg.tiles_x = (p.args.wout + G::TW - 1) / G::TW;
+        p.tg.tiles_y = (p.args.hout + G::TH - 1) / G::TH;
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
-        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.args, p.tg);
+        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.tA, p.tB, p.tU, p.tH, p.args, p.tg);
         return cudaGetLastError();
     }
     static cudaError_t launch(ConvPlan& p, int B, int prec, cudaStream_t st) {
-        if (p.cfg == 4) return prec == PREC_TF32 ? launch_cfg<4, PREC_TF32>(p, B, st) : launch_cfg<4, PREC_FP32X3>(p, B, st);
-        return prec == PREC_TF32 ? launch_cfg<2, PREC_TF32>(p, B, st) : launch_cfg<2, PREC_FP32X3>(p, B, st);
+        return prec == PREC_TF32 ? launch_prec<PREC_TF32>(p, B, st) : launch_prec<PREC_FP32X3>(p, B, st);
     }
 };
 

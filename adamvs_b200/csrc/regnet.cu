@@ -416,16 +416,15 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
                 && Gates2::plan(p5, a5, B, 1) && Cand2::plan(p6, a6, B, 1);
         tma = ok;
     }
-    // Which layers run on the tensor cores.  AUTO: measured per layer on B200 (profiles/r01s): the tcgen05 kernels need
-    // ~2 waves of 32x15 tiles to amortise their pipeline, conv1 (memory bound, one chunk per tile at stage 3) and the
-    // GRU-1 candidate conv (N = 16: the MMA is operand-fetch bound at any N <= 64) stay on the FFMA kernels.
+    // Which layers run on the tensor cores.  AUTO: measured per layer on B200 (profiles/r02g): with >= ~2 tiles per SM the
+    // tcgen05 kernels beat the FFMA kernels on every layer (stage 3, B = 8: 53/131/111/105/65 us against 69/279/155/267/161);
+    // smaller planes keep the split-K FFMA kernels, which spread one plane over all SMs.
     const int prec = math_mode == ADAMVS_MATH_TC_TF32 ? PREC_TF32 : PREC_FP32X3;
     const long long px = (long long)h * w * B;
     const bool all_tc = tma && (math_mode == ADAMVS_MATH_TC_FP32 || math_mode == ADAMVS_MATH_TC_TF32);
     const bool auto_tc = tma && math_mode == ADAMVS_MATH_AUTO;
-    const bool tc1 = all_tc, tc3 = all_tc;
-    const bool tc2 = all_tc || (auto_tc && px >= 400000), tc5 = tc2;
-    const bool tc6 = all_tc || (auto_tc && px >= 1500000);
+    const bool tc_full = all_tc || (auto_tc && px >= 30000), tc_half = all_tc || (auto_tc && px / 4 >= 30000);
+    const bool tc1 = tc_full, tc2 = tc_full, tc3 = tc_full, tc5 = tc_half, tc6 = tc_half;
     ConvPlan q1, q2, q3, q5, q6;
     {
         bool ok = true;

@@ -30,10 +30,10 @@ def main():
         ops.regnet_red(vol, wd, hyp, up, ops.PROB_SOFTMAX, math=ops.MATH_TC_FP32)
     torch.cuda.synchronize()
     L = ops.lib()
-    buf = np.zeros((3, 512, 4), dtype=np.int64)
+    buf = np.zeros((4, 512, 4), dtype=np.int64)
     rc = L.adamvs_tc_trace_read(buf.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0, rc
-    conv, mma, epi = buf
+    conv, mma, epi, ex = buf
     t0 = min(int(conv[0, 0]), int(mma[0, 0]))
     n = int((mma[:, 2] > 0).sum())
     print(f"chunks traced: {n}")
@@ -46,7 +46,8 @@ def main():
     print("tile | epi: top  got_acc  done")
     for t in range(min(nt, 20)):
         e = [int(x) - t0 for x in epi[t][:3]]
-        print(f"{t:4d} | {e[0]:8d} {e[1]:8d} {e[2]:8d}")
+        x = [int(v) - t0 for v in ex[t][:3]]
+        print(f"{t:4d} | {e[0]:8d} {e[1]:8d} {e[2]:8d} | step0: tmem {x[0]:8d} math {x[1]:8d} stored {x[2]:8d}")
     if n > 8:
         print("steady state clk/chunk (mma issued):", (int(mma[n - 1, 2]) - int(mma[4, 2])) / (n - 5))
         d_wait = (conv[5:n, 1] - conv[5:n, 0]).mean(); d_store = (conv[5:n, 2] - conv[5:n, 1]).mean(); d_fetch = (conv[5:n, 3] - conv[5:n, 2]).mean()
