@@ -32,6 +32,82 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st) {
     ADAMVS_LAUNCH_RESULT();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// adamvs_context_head_f32 - FeatureNet0's three output heads (reference models/adamvs.py:112-149):
+//     out = conv1x1(cat(upsample(a), upsample(c), x))          a, c: pooled-context maps at 1/4 and 1/8 of x's size
+// in one pass over x: the reference materialises both bilinear upsamplings and the concatenation (4.5x the bytes of x)
+// before a cuDNN 1x1 convolution; here a thread owns PX x-adjacent pixels and all COUT outputs, interpolates the
+// CCTX + CCTX context channels from the (L1/L2-resident) small maps in registers and reads x once.
+// Bilinear weights as ATen's upsample_bilinear2d, align_corners = False.
+// ------------------------------------------------------------------------------------------------------------------
+template <int CX, int CCTX, int COUT, int PX>
+__global__ void __launch_bounds__(128)
+context_head_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ c,
+                    const float* __restrict__ wgt, float* __restrict__ out, int h, int w, int ha, int wa, int hc, int wc) {
+    constexpr int CIN = 2 * CCTX + CX;
+    __shared__ float sW[CIN * COUT];                                   // [ci][co]
+    for (int i = threadIdx.x; i < CIN * COUT; i += 128) sW[i] = __ldg(wgt + (size_t)(i % COUT) * CIN + i / COUT);
+    __syncthreads();
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * PX, y = blockIdx.y, n = blockIdx.z;
+    if (x0 >= w) return;                                               // w % PX == 0: a group is all in or all out
+    float acc[PX][COUT];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[p][co] = 0.f;
+    // context channels: cat order is (a, c, x)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const float* src = m == 0 ? a : c;
+        const int hs = m == 0 ? ha : hc, ws = m == 0 ? wa : wc;
+        const Lerp ly = lerp_index(y, (float)hs / (float)h, hs);
+        const float* base = src + (size_t)n * CCTX * hs * ws;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const Lerp lx = lerp_index(x0 + p, (float)ws / (float)w, ws);
+#pragma unroll
+            for (int j = 0; j < CCTX; ++j) {
+                const float* pl = base + (size_t)j * hs * ws;
+                const float v00 = __ldg(pl + ly.i0 * ws + lx.i0), v01 = __ldg(pl + ly.i0 * ws + lx.i1);
+                const float v10 = __ldg(pl + ly.i1 * ws + lx.i0), v11 = __ldg(pl + ly.i1 * ws + lx.i1);
+                const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+                const float* wr = sW + (m * CCTX + j) * COUT;
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[p][co] = fmaf(v, wr[co], acc[p][co]);
+            }
+        }
+    }
+    const size_t hw = (size_t)h * w;
+    const float* px = x + (size_t)n * CX * hw + (size_t)y * w + x0;
+#pragma unroll 4
+    for (int ci = 0; ci < CX; ++ci) {
+        float v[PX];
+        if (PX == 4) { const float4 t = *reinterpret_cast<const float4*>(px + (size_t)ci * hw); v[0] = t.x; v[1] = t.y; v[2 % PX] = t.z; v[3 % PX] = t.w; }
+        else { const float2 t = *reinterpret_cast<const float2*>(px + (size_t)ci * hw); v[0] = t.x; v[1] = t.y; }
+        const float* wr = sW + (2 * CCTX + ci) * COUT;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float wv = wr[co];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[p][co] = fmaf(v[p], wv, acc[p][co]);
+        }
+    }
+    float* po = out + (size_t)n * COUT * hw + (size_t)y * w + x0;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        if (PX == 4) *reinterpret_cast<float4*>(po + (size_t)co * hw) = make_float4(acc[0][co], acc[1][co], acc[2 % PX][co], acc[3 % PX][co]);
+        else *reinterpret_cast<float2*>(po + (size_t)co * hw) = make_float2(acc[0][co], acc[1][co]);
+    }
+}
+
+template <int CX, int CCTX, int COUT, int PX>
+static int launch_context_head(const float* x, const float* a, const float* c, const float* wgt, float* out,
+                               int N, int h, int w, int ha, int wa, int hc, int wc, cudaStream_t st) {
+    dim3 grid((w / PX + 127) / 128, h, N);
+    context_head_kernel<CX, CCTX, COUT, PX><<<grid, 128, 0, st>>>(x, a, c, wgt, out, h, w, ha, wa, hc, wc);
+    ADAMVS_LAUNCH_RESULT();
+}
+
 }  // namespace adamvs
 
 using namespace adamvs;
@@ -143,4 +219,20 @@ extern "C" int adamvs_deconv3x3_f32(const float* in, const float* wpk, const flo
     if (CIN == 32) return launch_deconv<32, 16>(in, wpk, bias, relu, out, N, hin, win, st);
     if (CIN == 16) return launch_deconv<16, 8>(in, wpk, bias, relu, out, N, hin, win, st);
     return launch_deconv<48, 48>(in, wpk, bias, relu, out, N, hin, win, st);
+}
+
+extern "C" int adamvs_context_head_supported(int CX, int CCTX, int COUT) {
+    return (CX == 32 && CCTX == 16 && COUT == 32) || (CX == 16 && CCTX == 8 && COUT == 16) || (CX == 8 && CCTX == 4 && COUT == 8);
+}
+
+extern "C" int adamvs_context_head_f32(const float* x, const float* ctx_a, const float* ctx_c, const float* weight, float* out,
+                                       int N, int CX, int CCTX, int COUT, int h, int w, int ha, int wa, int hc, int wc, void* stream) {
+    ADAMVS_CHECK_ARG(x && ctx_a && ctx_c && weight && out && N > 0 && N <= 65535 && h > 0 && h <= 65535 && w > 0);
+    ADAMVS_CHECK_ARG(ha > 0 && wa > 0 && hc > 0 && wc > 0 && w % 4 == 0);
+    ADAMVS_CHECK_ARG(adamvs_context_head_supported(CX, CCTX, COUT));
+    ADAMVS_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (CX == 32) return launch_context_head<32, 16, 32, 2>(x, ctx_a, ctx_c, weight, out, N, h, w, ha, wa, hc, wc, st);
+    if (CX == 16) return launch_context_head<16, 8, 16, 4>(x, ctx_a, ctx_c, weight, out, N, h, w, ha, wa, hc, wc, st);
+    return launch_context_head<8, 4, 8, 4>(x, ctx_a, ctx_c, weight, out, N, h, w, ha, wa, hc, wc, st);
 }

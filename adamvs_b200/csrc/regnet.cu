@@ -129,13 +129,25 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
     for (int i = tid; i < 16 * 9 * 8; i += 256) sWu[i] = __ldg(wpk_up + i);
     if (tid < 72) sWo[tid] = __ldg(ow.w + tid);
     if (tid == 72) sWo[72] = __ldg(ow.b);
-    for (int i = tid; i < 16 * G::HH * (G::QW + 1); i += 256) {
-        const int cx = i % (G::QW + 1), rc = i / (G::QW + 1);
-        const int ry = rc % G::HH, c = rc / G::HH;
-        const int gy = qy0 + ry, gx = qx0 + cx;
-        float v = 0.f;
-        if (gy >= 0 && gy < h2 && gx >= 0 && gx < w2) v = __ldg(h2s + ((size_t)b * 16 + c) * hw2 + (size_t)gy * w2 + gx);
-        sH2[(c * G::HH + ry) * G::HP + cx] = v;
+    {   // h2 patch: all of a thread's loads in flight before its first shared-memory store
+        constexpr int NE = 16 * G::HH * (G::QW + 1), NI = (NE + 255) / 256;
+        float hv[NI];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int i = tid + 256 * j;
+            const int cx = i % (G::QW + 1), rc = i / (G::QW + 1);
+            const int ry = rc % G::HH, c = rc / G::HH;
+            const int gy = qy0 + ry, gx = qx0 + cx;
+            hv[j] = (i < NE && gy >= 0 && gy < h2 && gx >= 0 && gx < w2) ? __ldg(h2s + ((size_t)b * 16 + c) * hw2 + (size_t)gy * w2 + gx) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int i = tid + 256 * j;
+            if (i >= NE) break;
+            const int cx = i % (G::QW + 1), rc = i / (G::QW + 1);
+            const int ry = rc % G::HH, c = rc / G::HH;
+            sH2[(c * G::HH + ry) * G::HP + cx] = hv[j];
+        }
     }
     __syncthreads();
 
@@ -143,21 +155,26 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
     if (tid < G::QH * G::QW) {
         const int qy = tid / G::QW, qx = tid - qy * G::QW;
         float acc[4][8];
+        // bias + skip connection h1 of the four pixels: requested now, consumed after the FFMA loop
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
+            const int fy = 2 * (qy0 + qy) + (q >> 1), fx = 2 * (qx0 + qx) + (q & 1);
+            const bool in = fy >= 0 && fy < h && fx >= 0 && fx < w;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+            for (int c = 0; c < 8; ++c)
+                acc[q][c] = in ? __ldg(up_b + c) + __ldg(h1 + ((size_t)b * 8 + c) * hw + (size_t)fy * w + fx) : 0.f;
+        }
 #pragma unroll 4
         for (int ci = 0; ci < 16; ++ci) {
             const float* p = sH2 + (ci * G::HH + qy) * G::HP + qx;
             const float v00 = p[0], v01 = p[1], v10 = p[G::HP], v11 = p[G::HP + 1];
             const float* wt = sWu + ci * 72;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                acc[0][c] += v00 * wt[4 * 8 + c];
-                acc[1][c] += v01 * wt[3 * 8 + c] + v00 * wt[5 * 8 + c];
-                acc[2][c] += v10 * wt[1 * 8 + c] + v00 * wt[7 * 8 + c];
-                acc[3][c] += v11 * wt[0 * 8 + c] + v10 * wt[2 * 8 + c] + v01 * wt[6 * 8 + c] + v00 * wt[8 * 8 + c];
+            for (int c = 0; c < 8; ++c) {                                                 // 9 FFMA, nothing else
+                acc[0][c] = fmaf(v00, wt[4 * 8 + c], acc[0][c]);
+                acc[1][c] = fmaf(v00, wt[5 * 8 + c], fmaf(v01, wt[3 * 8 + c], acc[1][c]));
+                acc[2][c] = fmaf(v00, wt[7 * 8 + c], fmaf(v10, wt[1 * 8 + c], acc[2][c]));
+                acc[3][c] = fmaf(v00, wt[8 * 8 + c], fmaf(v01, wt[6 * 8 + c], fmaf(v10, wt[2 * 8 + c], fmaf(v11, wt[0 * 8 + c], acc[3][c]))));
             }
         }
 #pragma unroll
@@ -167,11 +184,8 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
             if (ry < 0 || ry >= G::YH || rx < 0 || rx >= G::YW) continue;
             const bool in = fy >= 0 && fy < h && fx >= 0 && fx < w;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v = 0.f;                                                            // outside the image: the output layer's zero padding
-                if (in) v = fmaxf(acc[q][c] + __ldg(up_b + c) + __ldg(h1 + ((size_t)b * 8 + c) * hw + (size_t)fy * w + fx), 0.f);
-                sY[(c * G::YH + ry) * G::YP + rx] = v;
-            }
+            for (int c = 0; c < 8; ++c)                                                   // outside the image: the output layer's zero padding
+                sY[(c * G::YH + ry) * G::YP + rx] = in ? fmaxf(acc[q][c], 0.f) : 0.f;
         }
     }
     __syncthreads();
@@ -192,18 +206,39 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
                 lg[0] = fmaf(v0, wt[0], fmaf(v1, wt[1], fmaf(v2, wt[2], lg[0])));
                 lg[1] = fmaf(v1, wt[0], fmaf(v2, wt[1], fmaf(v3, wt[2], lg[1])));
             }
+        RegressAcc ra[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x < w) ra[e] = regress_load(st, (size_t)b * hw + y0 * w + x, k, prob_mode);
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int x = ox0 + tx + e;
             if (x >= w) continue;
             const int pix = y0 * w + x;
-            const size_t o = (size_t)b * hw + pix;
             if (logits_out) logits_out[((size_t)b * D + k) * hw + pix] = lg[e];
-            regress_update(st, o, lg[e], hyp_at(hyp_line(hs, b, pix, (int)hw, D), k), k, D, prob_mode, depth, conf);
+            regress_step(ra[e], lg[e], hyp_at(hyp_line(hs, b, pix, (int)hw, D), k), prob_mode);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x < w) regress_store(st, (size_t)b * hw + y0 * w + x, ra[e], k, D, prob_mode, depth, conf);
         }
     } else {
         const int Ho = 2 * h, Wo = 2 * w;
         const size_t ohw = (size_t)Ho * Wo;
+        // 2 quads x 4 output pixels per thread: regression states first, logits and hypotheses next, stores last
+        RegressAcc ra[2][4];
+        float lg[2][4], dv[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x >= w) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                ra[e][q] = regress_load(st, (size_t)b * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1), k, prob_mode);
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int x = ox0 + tx + e;
@@ -214,29 +249,37 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
                 const float* p = sY + (ci * G::YH + ty) * G::YP + tx + e;
                 const float v00 = p[0], v01 = p[1], v10 = p[G::YP], v11 = p[G::YP + 1];   // zero beyond the image (phase A)
                 const float* wt = sWo + ci * 9;
-                l00 += v00 * wt[4];
-                l01 += v01 * wt[3] + v00 * wt[5];
-                l10 += v10 * wt[1] + v00 * wt[7];
-                l11 += v11 * wt[0] + v10 * wt[2] + v01 * wt[6] + v00 * wt[8];
+                l00 = fmaf(v00, wt[4], l00);
+                l01 = fmaf(v00, wt[5], fmaf(v01, wt[3], l01));
+                l10 = fmaf(v00, wt[7], fmaf(v10, wt[1], l10));
+                l11 = fmaf(v00, wt[8], fmaf(v01, wt[6], fmaf(v10, wt[2], fmaf(v11, wt[0], l11))));
             }
-            const float lg[4] = {l00, l01, l10, l11};
+            lg[e][0] = l00; lg[e][1] = l01; lg[e][2] = l10; lg[e][3] = l11;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int oy = 2 * y0 + (q >> 1), ox = 2 * x + (q & 1);
-                float dval;
                 if (hs.mode == ADAMVS_HYP_PLANES) {
-                    dval = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
+                    dv[e][q] = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
                 } else {
                     const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
                     const float d00 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i0, (int)hw, D), k);
                     const float d01 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i1, (int)hw, D), k);
                     const float d10 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i0, (int)hw, D), k);
                     const float d11 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i1, (int)hw, D), k);
-                    dval = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
+                    dv[e][q] = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
                 }
-                const size_t o = (size_t)b * ohw + (size_t)oy * Wo + ox;
-                if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)oy * Wo + ox] = lg[q];
-                regress_update(st, o, lg[q], dval, k, D, prob_mode, depth, conf);
+                regress_step(ra[e][q], lg[e][q], dv[e][q], prob_mode);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = ox0 + tx + e;
+            if (x >= w) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const size_t o = (size_t)b * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1);
+                if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1)] = lg[e][q];
+                regress_store(st, o, ra[e][q], k, D, prob_mode, depth, conf);
             }
         }
     }

@@ -44,6 +44,42 @@ __device__ __forceinline__ void regress_update(const RegressState& st, size_t o,
     st.s0[o] = a0; st.s1[o] = a1; st.s2[o] = a2;
 }
 
+// The same update in three phases, for kernels that handle several pixels per thread: the compiler does not move a
+// global load above an earlier global store, so load -> exp -> store per pixel serialises the pixels' L2 round trips;
+// all loads first, all stores last keeps them in flight together.
+struct RegressAcc { float a0, a1, a2; };
+
+__device__ __forceinline__ RegressAcc regress_load(const RegressState& st, size_t o, int k, int prob_mode) {
+    RegressAcc r;
+    if (k == 0) { r.a0 = prob_mode == ADAMVS_PROB_SOFTMAX ? -INFINITY : 0.f; r.a1 = 0.f; r.a2 = 0.f; }
+    else { r.a0 = st.s0[o]; r.a1 = st.s1[o]; r.a2 = st.s2[o]; }
+    return r;
+}
+__device__ __forceinline__ void regress_step(RegressAcc& r, float logit, float dval, int prob_mode) {
+    if (prob_mode == ADAMVS_PROB_SOFTMAX) {
+        const float m = fmaxf(r.a0, logit);
+        const float scale = expf(r.a0 - m);         // 0 when a0 = -inf
+        const float e = expf(logit - m);
+        r.a1 = r.a1 * scale + e;
+        r.a2 = r.a2 * scale + dval * e;
+        r.a0 = m;
+    } else {
+        const float e = expf(logit);
+        r.a0 = (r.a0 < e) ? e : r.a0;               // adamvs.py:518-519
+        r.a2 = dval * e + r.a2;                     // adamvs.py:524
+        r.a1 = r.a1 + e;                            // adamvs.py:527
+    }
+}
+__device__ __forceinline__ void regress_store(const RegressState& st, size_t o, const RegressAcc& r, int k, int D, int prob_mode,
+                                              float* depth, float* conf) {
+    if (k == D - 1) {
+        if (prob_mode == ADAMVS_PROB_SOFTMAX) { depth[o] = r.a2 / r.a1; conf[o] = 1.f / r.a1; }
+        else { const float den = r.a1 + 1e-10f; depth[o] = r.a2 / den; conf[o] = r.a0 / den; }
+        return;
+    }
+    st.s0[o] = r.a0; st.s1[o] = r.a1; st.s2[o] = r.a2;
+}
+
 // logit = conv3x3(y [+ y2]; 8->1) + b at the same resolution.  `flip` reads the taps mirrored, which turns the
 // correlation into PyTorch's stride-1 ConvTranspose2d (MS-REDNet's output layer, models/msrednet.py:351).
 template <bool HAS_Y2, bool FLIP>

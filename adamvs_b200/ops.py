@@ -28,6 +28,7 @@ EXPORTS = (
     "adamvs_softmax_regress_f32", "adamvs_variance_volume_f32", "adamvs_regnet_msred_workspace_floats",
     "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
     "adamvs_deconv3x3_supported", "adamvs_deconv3x3_f32",
+    "adamvs_context_head_supported", "adamvs_context_head_f32",
 )
 
 
@@ -78,6 +79,8 @@ def lib() -> ctypes.CDLL:
         L.adamvs_deconv3x3_supported.argtypes = [ci, ci]
         L.adamvs_deconv3x3_f32.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv3x3_supported.argtypes = [ci, ci, ci, ci]
+        L.adamvs_context_head_supported.argtypes = [ci, ci, ci]
+        L.adamvs_context_head_f32.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv3x3_f32.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, vp]
         for name in EXPORTS:
             if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats",
@@ -335,6 +338,28 @@ def conv3x3(xa: torch.Tensor, xb: Optional[torch.Tensor], wpk: torch.Tensor, bia
     with _timed("conv3x3", 1):
         _check(lib().adamvs_conv3x3_f32(_p(xa), CA, _p(xb), CB, _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu),
                                         int(stride), _p(out), N, COUT, h, w, _stream()), "conv3x3")
+    return out
+
+
+def context_head_supported(cx: int, cctx: int, cout: int) -> bool:
+    return bool(lib().adamvs_context_head_supported(int(cx), int(cctx), int(cout)))
+
+
+def context_head(x: torch.Tensor, ctx_a: torch.Tensor, ctx_c: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """conv1x1(cat(up(ctx_a), up(ctx_c), x), weight) with up() = bilinear resize to x's size (align_corners=False):
+    x [N,CX,h,w], ctx_a / ctx_c [N,CCTX,*,*], weight [COUT, 2*CCTX+CX(,1,1)] -> [N,COUT,h,w]."""
+    x, ctx_a, ctx_c = _f32c(x, "x"), _f32c(ctx_a, "ctx_a"), _f32c(ctx_c, "ctx_c")
+    N, CX, h, w = x.shape
+    CCTX = ctx_a.shape[1]
+    COUT = weight.shape[0]
+    wt = _f32c(weight.reshape(COUT, -1), "weight")
+    if ctx_c.shape[1] != CCTX or wt.shape[1] != 2 * CCTX + CX or ctx_a.shape[0] != N or ctx_c.shape[0] != N:
+        raise ValueError("context_head: inconsistent shapes")
+    out = torch.empty((N, COUT, h, w), device=x.device, dtype=torch.float32)
+    with _timed("context_head", 1):
+        _check(lib().adamvs_context_head_f32(_p(x), _p(ctx_a), _p(ctx_c), _p(wt), _p(out), N, CX, CCTX, COUT, h, w,
+                                             ctx_a.shape[2], ctx_a.shape[3], ctx_c.shape[2], ctx_c.shape[3], _stream()),
+               "context_head")
     return out
 
 

@@ -190,6 +190,15 @@ int adamvs_conv3x3_supported(int CA, int CB, int COUT, int stride);
 int adamvs_conv3x3_f32(const float* inA, int CA, const float* inB, int CB, const float* wpk, const float* bias,
                        int relu, int stride, float* out, int N, int COUT, int hin, int win, void* stream);
 
+/* FeatureNet0's output heads (adamvs.py:112-149): out = conv1x1(cat(up(ctx_a), up(ctx_c), x), weight), where up() is the
+ * bilinear resize (align_corners = False, F.upsample / F.interpolate) of the pooled-context maps to x's size; replaces the
+ * two interpolations, the concatenation and the bias-free 1x1 Conv2d out1/out2/out3.
+ * x [N,CX,h,w]; ctx_a [N,CCTX,ha,wa]; ctx_c [N,CCTX,hc,wc]; weight [COUT][2*CCTX+CX] (the Conv2d weight, cat order a, c, x);
+ * out [N,COUT,h,w].  w % 4 == 0.  Channel combinations: adamvs_context_head_supported(). */
+int adamvs_context_head_supported(int CX, int CCTX, int COUT);
+int adamvs_context_head_f32(const float* x, const float* ctx_a, const float* ctx_c, const float* weight, float* out,
+                            int N, int CX, int CCTX, int COUT, int h, int w, int ha, int wa, int hc, int wc, void* stream);
+
 /* out = act(convT3x3 stride 2, padding 1, output_padding 1 (in; CIN -> COUT) + bias); replaces Deconv2d + BatchNorm (eval,
  * folded by the caller) + ReLU (module.py:202-245) and CostRegNet2D's transposed blocks (adamvs.py:212-225).
  * in [N,CIN,hin,win]; wpk: ConvTranspose2d weight [CIN,COUT,3,3] re-laid as [CIN][9][COUT]; out [N,COUT,2hin,2win]. */

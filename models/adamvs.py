@@ -168,6 +168,10 @@ class FeatureNet0(nn.Module):
     @staticmethod
     def _head(x, br_a, br_b, proj):
         size = x.shape[2:]
+        if (_NATIVE_CONV and not proj.training and x.is_cuda and x.dtype == torch.float32 and x.shape[3] % 4 == 0
+                and _ops.context_head_supported(x.shape[1], br_a[1].conv.out_channels, proj.out_channels)):
+            # both upsamplings, the concatenation and the 1x1 projection in one pass over x (adamvs_context_head_f32)
+            return _ops.context_head(x, br_a(x), br_b(x), proj.weight)
         a = F.interpolate(br_a(x), size=size, mode="bilinear", align_corners=False)
         c = F.interpolate(br_b(x), size=size, mode="bilinear", align_corners=False)
         return proj(torch.cat((a, c, x), 1))

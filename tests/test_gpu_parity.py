@@ -554,6 +554,24 @@ def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
     assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("cx,cctx,cout,h,w", [(32, 16, 32, 24, 48), (16, 8, 16, 48, 96), (8, 4, 8, 96, 192), (8, 4, 8, 40, 72)])
+def test_context_head_vs_torch(cx, cctx, cout, h, w):
+    """FeatureNet0's output heads fused (both bilinear upsamplings + cat + 1x1 conv) against the torch ops the reference
+    uses (F.interpolate align_corners=False, torch.cat, F.conv2d) in fp32 on the CPU."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cx + h)
+    N = 3
+    x = torch.randn(N, cx, h, w, generator=g)
+    a = torch.randn(N, cctx, h // 4, w // 4, generator=g)
+    c = torch.randn(N, cctx, h // 8, w // 8, generator=g)
+    wt = torch.randn(cout, 2 * cctx + cx, 1, 1, generator=g) / (2 * cctx + cx) ** 0.5
+    up = lambda t: F.interpolate(t, size=(h, w), mode="bilinear", align_corners=False)
+    want = F.conv2d(torch.cat((up(a), up(c), x), 1), wt)
+    got = ops.context_head(x.to(_dev()), a.to(_dev()), c.to(_dev()), wt.to(_dev())).cpu()
+    assert tuple(got.shape) == tuple(want.shape)
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
 @pytest.mark.parametrize("cin,cout,h,w", [(32, 16, 12, 20), (16, 8, 24, 36), (48, 48, 6, 10)])
 def test_native_deconv3x3_vs_torch(cin, cout, h, w):
     ops = _ops()
