@@ -4,6 +4,8 @@
 // BatchNorm is folded into weights and bias by the caller, ReLU is fused, and a channel concatenation in front
 // of the conv (DeConv2dFuse, module.py:506-524) is read as two tensors instead of being materialised.
 #include "conv3x3.cuh"
+#include "conv3x3_tc.cuh"
+#include <string.h>
 
 namespace adamvs {
 
@@ -13,6 +15,23 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st) {
     using L = ConvLayer<CA, CB, COUT, COB, STRIDE, EPI_BIAS>;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.inA) | reinterpret_cast<uintptr_t>(a.inB) |
                            reinterpret_cast<uintptr_t>(a.out0)) % 16) == 0;
+    // Stride-1 layers with enough pixels for ~2 tiles per SM run on the tensor cores (conv3x3_tc.cuh: kind::tf32 with the
+    // exact hi/lo operand split, fp32 accuracy): 4-5x the FFMA kernels on the 16- and 32-channel layers.
+    // ADAMVS_CONV2D_MATH=ffma (or a forced ADAMVS_CONV_CFG) keeps the FFMA kernels - test / measurement hook.
+    static const bool tc_allowed = [] {
+        const char* e = getenv("ADAMVS_CONV2D_MATH");
+        return !(e && !strcmp(e, "ffma")) && getenv("ADAMVS_CONV_CFG") == nullptr;
+    }();
+    if constexpr (STRIDE == 1 && COUT <= 32) {                         // 48 output channels: N = 288 exceeds one MMA
+        if (tc_allowed && aligned && a.win % 4 == 0 && (long long)N * a.hout * a.wout >= 30000) {
+            using T = TcLayer<CA, CB, COUT, EPI_BIAS>;
+            ConvPlan p;
+            if (T::plan(p, a, N, 1)) {
+                cudaError_t e = T::launch(p, N, PREC_FP32X3, st);
+                return e == cudaSuccess ? 0 : (int)e;
+            }
+        }
+    }
     if (aligned && a.win % 4 == 0 && a.wout % 4 == 0) {
         ConvPlan p;
         if (L::plan(p, a, N, 1)) {

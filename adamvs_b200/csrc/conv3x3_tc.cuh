@@ -45,7 +45,7 @@ enum { PREC_FP32X3 = 0, PREC_TF32 = 1 };
 // Debug builds only (ADAMVS_TC_TRACE=1 python adamvs_b200/build.py --force): block 0 of the GRU-1 gate convolution
 // records clock64() stamps of its three roles; tools/tc_trace.py prints the timeline.
 #ifdef ADAMVS_TC_TRACE
-__device__ long long g_tc_trace[4][512][4];
+static __device__ long long g_tc_trace[4][512][4];
 #define TC_TRACE(role, idx, f) do { if (CA == 8 && CB == 8 && COUT == 16 && PREC == PREC_FP32X3 && blockIdx.x == 0 && (idx) < 512) g_tc_trace[role][idx][f] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, idx, f) do { } while (0)

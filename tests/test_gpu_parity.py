@@ -535,10 +535,14 @@ def test_regnet_red_tensor_core_vs_oracle(C, D, h, w, up, prob):
 @pytest.mark.parametrize("ca,cb,cout,stride,relu,h,w", [
     (8, 0, 8, 1, True, 40, 64), (16, 0, 16, 1, True, 36, 52), (32, 0, 32, 1, True, 24, 32), (16, 16, 16, 1, True, 32, 64),
     (8, 8, 8, 1, True, 64, 96), (48, 0, 48, 1, False, 24, 48), (48, 0, 48, 2, True, 24, 48), (48, 0, 48, 1, True, 18, 30),
-    (32, 0, 16, 1, True, 64, 96), (64, 0, 32, 1, True, 32, 48), (64, 0, 32, 1, True, 30, 44)])
+    (32, 0, 16, 1, True, 64, 96), (64, 0, 32, 1, True, 32, 48), (64, 0, 32, 1, True, 30, 44),
+    # >= 30000 pixels: the stride-1 layers switch to the tcgen05 kernel (ragged tiles: 100 = 3 x 30 + 10 columns, 106 rows)
+    (8, 0, 8, 1, True, 106, 100), (16, 0, 16, 1, True, 106, 100), (32, 0, 32, 1, False, 106, 100), (16, 16, 16, 1, True, 106, 100),
+    (8, 8, 8, 1, True, 106, 100), (32, 0, 16, 1, True, 106, 100), (64, 0, 32, 1, True, 106, 100)])
 def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
-    """The 3x3 convolutions of FeatureNet0 / CostRegNet2D on the FFMA kernels (TMA and generic-tile paths) against
-    F.conv2d in fp32 on the CPU: same math, different summation order."""
+    """The 3x3 convolutions of FeatureNet0 / CostRegNet2D on the native kernels (FFMA: TMA and generic-tile paths;
+    tcgen05 with the exact hi/lo tf32 split for large stride-1 layers) against F.conv2d in fp32 on the CPU: same math,
+    different summation order."""
     ops = _ops()
     g = torch.Generator().manual_seed(ca + cout + h)
     N = 3
