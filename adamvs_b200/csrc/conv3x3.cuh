@@ -252,11 +252,17 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tx = t % (TW / PX), ty = t / (TW / PX);
     const int cob = blockIdx.y;
 
+    pdl_launch_dependents();
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < G::W_FLOATS; i += G::NT) {                 // resident weights, once per CTA
+        const int col = i % COB, ct = i / COB;
+        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
+    }
+    pdl_wait();                                                      // activations of the preceding kernel from here on
     __syncthreads();
 
     const int my_tiles = (tg.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -283,11 +289,6 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (tid == 0) {
         for (int g = 0; g < NSTAGE - 1 && g < total; ++g) issue(g);
     }
-    for (int i = tid; i < G::W_FLOATS; i += G::NT) {                 // resident weights, once per CTA
-        const int col = i % COB, ct = i / COB;
-        sW[i] = __ldg(a.wpk + (size_t)ct * COUT + cob * COB + col);
-    }
-    __syncthreads();
 
     int g = 0;
 #pragma unroll 1
@@ -510,8 +511,7 @@ static cudaError_t launch_v2(ConvPlan& p, int B, cudaStream_t st) {
     if (ctas < 1) ctas = 1;
     if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
     dim3 grid(ctas, ncob, 1);
-    kern<<<grid, G::NT, G::SMEM, st>>>(p.tA, p.tB, p.args, p.tg);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, dim3(G::NT), G::SMEM, st, p.tA, p.tB, p.args, p.tg);
 }
 
 // Ring depth: as many steps in flight as fit ~60 KB of shared memory per CTA (3-4 CTAs per SM), at least 2.

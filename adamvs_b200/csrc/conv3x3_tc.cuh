@@ -193,6 +193,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __shared__ float sBias[COUT];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -222,6 +223,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     fence_proxy_async();
     tc_fence_before();
+    pdl_wait();                                                              // the prologue above overlapped the previous kernel
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
@@ -477,8 +479,7 @@ struct TcLayer {
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
-        kern<<<dim3(ctas, 1, 1), kTcThreads, C::SMEM, st>>>(p.tA, p.tB, p.tU, p.tH, p.args, p.tg);
-        return cudaGetLastError();
+        return launch_pdl(kern, dim3(ctas, 1, 1), dim3(kTcThreads), C::SMEM, st, p.tA, p.tB, p.tU, p.tH, p.args, p.tg);
     }
     static cudaError_t launch(ConvPlan& p, int B, int prec, cudaStream_t st) {
         return prec == PREC_TF32 ? launch_prec<PREC_TF32>(p, B, st) : launch_prec<PREC_FP32X3>(p, B, st);

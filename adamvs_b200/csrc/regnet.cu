@@ -108,7 +108,7 @@ struct TailGeom {
 };
 
 template <bool UP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk_up, const float* __restrict__ up_b,
                     const float* __restrict__ h1, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
                     float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
@@ -126,9 +126,11 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
     const size_t hw = (size_t)h * w, hw2 = (size_t)h2 * w2;
     const int qy0 = oy0 / 2 - G::LO, qx0 = ox0 / 2 - G::LO;     // first half-resolution quad
 
+    pdl_launch_dependents();
     for (int i = tid; i < 16 * 9 * 8; i += 256) sWu[i] = __ldg(wpk_up + i);
     if (tid < 72) sWo[tid] = __ldg(ow.w + tid);
     if (tid == 72) sWo[72] = __ldg(ow.b);
+    pdl_wait();                                                  // weights above overlapped the previous kernel's tail
     {   // h2 patch: all of a thread's loads in flight before its first shared-memory store
         constexpr int NE = 16 * G::HH * (G::QW + 1), NI = (NE + 255) / 256;
         float hv[NI];
@@ -511,10 +513,9 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
         // 7+8: up1 + skip + relu -> output layer -> online regression, one launch
         {
             dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
-            if (out_up) tail_regress_kernel<true><<<grid, 256, 0, st>>>(ws.h2, ws.pk_up1, hwts->up1_b, ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
-            else tail_regress_kernel<false><<<grid, 256, 0, st>>>(ws.h2, ws.pk_up1, hwts->up1_b, ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w);
+            if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w));
+            else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w));
         }
-        ADAMVS_TRY(cudaGetLastError());
     }
     return 0;
 }
