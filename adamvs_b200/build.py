@@ -23,10 +23,6 @@ if os.environ.get("ADAMVS_TC_TRACE"):                # debug build: role timelin
 
 
 
-if os.environ.get("ADAMVS_TC_EXPERIMENT"):           # throw-away experiments inside the tcgen05 conv kernel
-    NVCC_FLAGS.append("-DADAMVS_TC_EXPERIMENT=" + os.environ["ADAMVS_TC_EXPERIMENT"])
-
-
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
