@@ -96,6 +96,17 @@ upconv_add_relu_kernel(const float* __restrict__ in, const float* __restrict__ w
 // ------------------------------------------------------------------------------------------------
 constexpr int kTailW = 32, kTailH = 16;
 
+// (lo, step) of every pixel's hypothesis line, once per sweep: the x2-upsampling tail blends four neighbours' hypotheses per
+// output pixel and plane, and evaluating hyp_line() there (two loads and an IEEE division per corner) was half of its
+// instructions.  Same values, computed once.
+__global__ void __launch_bounds__(256)
+hyp_lines_kernel(HypSpec hs, float2* __restrict__ out, int B, int hw, int D) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * hw) return;
+    const HypLine l = hyp_line(hs, i / hw, i % hw, hw, D);
+    out[i] = make_float2(l.lo, l.step);
+}
+
 template <bool UP>
 struct TailGeom {
     static constexpr int LO = UP ? 0 : 1;                       // halo before the tile
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(256, 3)
 tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk_up, const float* __restrict__ up_b,
                     const float* __restrict__ h1, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
                     float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
-                    int k, int D, int h, int w) {
+                    const float2* __restrict__ hlines, int k, int D, int h, int w) {
     using G = TailGeom<UP>;
     __shared__ float sH2[16 * G::HH * G::HP];
     __shared__ float sY[8 * G::YH * G::YP];
@@ -220,7 +231,10 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
             if (x >= w) continue;
             const int pix = y0 * w + x;
             if (logits_out) logits_out[((size_t)b * D + k) * hw + pix] = lg[e];
-            regress_step(ra[e], lg[e], hyp_at(hyp_line(hs, b, pix, (int)hw, D), k), prob_mode);
+            HypLine hl;
+            if (hlines) { const float2 t = __ldg(hlines + (size_t)b * hw + pix); hl = HypLine{t.x, t.y}; }
+            else hl = hyp_line(hs, b, pix, (int)hw, D);
+            regress_step(ra[e], lg[e], hyp_at(hl, k), prob_mode);
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -264,10 +278,15 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
                     dv[e][q] = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
                 } else {
                     const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
-                    const float d00 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i0, (int)hw, D), k);
-                    const float d01 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i1, (int)hw, D), k);
-                    const float d10 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i0, (int)hw, D), k);
-                    const float d11 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i1, (int)hw, D), k);
+                    auto line_at = [&](int p) {
+                        if (hlines == nullptr) return hyp_line(hs, b, p, (int)hw, D);
+                        const float2 t = __ldg(hlines + (size_t)b * hw + p);
+                        return HypLine{t.x, t.y};
+                    };
+                    const float d00 = hyp_at(line_at(ly.i0 * w + lx.i0), k);
+                    const float d01 = hyp_at(line_at(ly.i0 * w + lx.i1), k);
+                    const float d10 = hyp_at(line_at(ly.i1 * w + lx.i0), k);
+                    const float d11 = hyp_at(line_at(ly.i1 * w + lx.i1), k);
                     dv[e][q] = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
                 }
                 regress_step(ra[e][q], lg[e][q], dv[e][q], prob_mode);
@@ -434,6 +453,12 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
     ADAMVS_TRY(cudaMemsetAsync(ws.h2, 0, sizeof(float) * B * 16 * hw2, st));
     const OutWeights ow{hwts->out_w, hwts->out_b};
     const RegressState rs{ws.s0, ws.s1, ws.s2};
+    const float2* hlines = nullptr;                       // per-pixel hypothesis lines for the tail (in ws.y: y itself
+    if (hyp_mode == ADAMVS_HYP_PER_PIXEL) {               // never leaves shared memory since the tail was fused)
+        hyp_lines_kernel<<<(unsigned)(((size_t)B * hw + 255) / 256), 256, 0, st>>>(hs, reinterpret_cast<float2*>(ws.y), B, (int)hw, D);
+        ADAMVS_TRY(cudaGetLastError());
+        hlines = reinterpret_cast<const float2*>(ws.y);
+    }
 
     // ---- per-layer arguments (fixed for the whole sweep; only conv1's plane index changes)
     ConvArgs a1{}, a2{}, a3{}, a4{}, a5{}, a6{};
@@ -513,8 +538,8 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
         // 7+8: up1 + skip + relu -> output layer -> online regression, one launch
         {
             dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
-            if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w));
-            else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, k, D, h, w));
+            if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, hlines, k, D, h, w));
+            else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, hlines, k, D, h, w));
         }
     }
     return 0;

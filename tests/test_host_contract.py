@@ -46,6 +46,11 @@ def test_argument_errors_come_back_as_codes_without_touching_a_device():
     assert int(L.adamvs_regnet_red_workspace_floats(0, 8, 4, 8, 8, 0)) == 0
     assert int(L.adamvs_regnet_red_workspace_floats(1, 8, 4, 64, 96, 0)) > 8 * 64 * 96
     assert int(L.adamvs_regnet_msred_workspace_floats(1, 8, 4, 64, 96)) > 8 * 64 * 96
+    # the fused FeatureNet0 head: the three channel combinations of the reference's pyramid and nothing else
+    assert [L.adamvs_context_head_supported(*c) for c in ((32, 16, 32), (16, 8, 16), (8, 4, 8), (8, 8, 8), (64, 32, 64))] == [1, 1, 1, 0, 0]
+    assert L.adamvs_context_head_f32(None, None, None, None, None, 1, 8, 4, 8, 16, 16, 4, 4, 2, 2, None) == -1
+    # the arithmetic mode of the regulariser is validated before anything is launched
+    assert L.adamvs_regnet_red_ex_f32(None, None, 0, None, 2, None, 0, 0, 7, None, 0, None, None, None, 1, 8, 4, 8, 8, None) == -1
 
 
 def test_adamvs_drop_in_names_signatures_and_state_dict():
