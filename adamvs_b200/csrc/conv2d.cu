@@ -22,7 +22,23 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st) {
         const char* e = getenv("ADAMVS_CONV2D_MATH");
         return !(e && !strcmp(e, "ffma")) && getenv("ADAMVS_CONV_CFG") == nullptr;
     }();
-    if constexpr (STRIDE == 1 && COUT <= 32) {                         // 48 output channels: N = 288 exceeds one MMA
+    if constexpr (STRIDE == 1 && COUT == 48) {                         // N = 3 x 2 x 48 exceeds one MMA: two 24-channel slices
+        if (tc_allowed && aligned && a.win % 4 == 0 && (long long)N * a.hout * a.wout >= 30000) {
+            using T = TcLayer<CA, CB, 24, EPI_BIAS>;
+            ConvArgs h = a;
+            h.wpk_cout = 48; h.out_cout = 48;
+            ConvPlan p;
+            if (T::plan(p, h, N, 1)) {
+                for (int half = 0; half < 2; ++half) {
+                    p.args.co_off = 24 * half;
+                    cudaError_t e = T::launch(p, N, PREC_FP32X3, st);
+                    if (e != cudaSuccess) return (int)e;
+                }
+                return 0;
+            }
+        }
+    }
+    if constexpr (STRIDE == 1 && COUT <= 32) {
         if (tc_allowed && aligned && a.win % 4 == 0 && (long long)N * a.hout * a.wout >= 30000) {
             using T = TcLayer<CA, CB, COUT, EPI_BIAS>;
             ConvPlan p;

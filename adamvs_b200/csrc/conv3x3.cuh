@@ -30,6 +30,9 @@ struct ConvArgs {
     double* stats;         // RAW_STATS: [B][2][2] = per batch item, per channel half, {sum, sum of squares}
     int stats_split;       // RAW_STATS: 1 = two halves of COUT are separate groups (gate conv), 0 = one group
     int relu;              // BIAS: apply ReLU after the bias
+    // tensor-core kernels only: a launch may compute a slice [co_off, co_off + COUT) of a wider layer (48 output channels
+    // exceed one MMA's N): row length of wpk / channel count of the output tensor (0 = COUT), first channel of the slice
+    int wpk_cout, out_cout, co_off;
 };
 
 template <int STRIDE, int TW, int TH>

@@ -141,7 +141,7 @@ struct TcCfg {
     static constexpr int NA = 3;                                   // operand stages
     // GRU epilogue operands (h for the reset gates; u and h for the candidate blend) travel like the input: the producer
     // streams [channels][4*MT rows][32] boxes of the output tile into a ring EPI_R tiles deep
-    static constexpr int NGW = MT * (COUT / 8) / 2;                // epilogue steps per warp and tile
+    static constexpr int NGW = (MT * (COUT / 8) + 1) / 2;          // epilogue steps per warp and tile (the last may be empty)
     static constexpr int EPI_CH = EPI == EPI_GATES ? COUT / 2 : (EPI == EPI_CAND ? 2 * COUT : 0);
     static constexpr int EPI_PLANE = G::TH * 32;                   // floats per channel of a box
     static constexpr int EPI_TILE_BYTES = EPI_CH * EPI_PLANE * 4;
@@ -205,7 +205,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 3; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 8); }
         fence_mbar_init();
     }
-    if (tid < COUT) sBias[tid] = (EPI == EPI_RELU || a.bias == nullptr) ? 0.f : __ldg(a.bias + tid);
+    const int wrow = a.wpk_cout > 0 ? a.wpk_cout : COUT, ocout = a.out_cout > 0 ? a.out_cout : COUT;   // slice of a wider layer
+    if (tid < COUT) sBias[tid] = (EPI == EPI_RELU || a.bias == nullptr) ? 0.f : __ldg(a.bias + a.co_off + tid);
     // resident weights: [ci][tap][co] -> B operand [ky][chunk][quad][kx: W_hi co | W_lo co][4 ci], split once per CTA
     for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += kTcThreads) {
         int r = i;
@@ -214,7 +215,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kx = r % 3; r /= 3;
         const int kq = r & 1; r >>= 1;
         const int s = r % C::NCH, ky = r / C::NCH;
-        const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + ky * 3 + kx) * COUT + n);
+        const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + ky * 3 + kx) * wrow + a.co_off + n);
         float hi, lo;
         split_tf32(v, hi, lo);
         float* dst = reinterpret_cast<float*>(sB + (size_t)(ky * C::NCH + s) * C::B_STEP_BYTES + kq * C::N3 * 16) + kx * C::NB * 4;
@@ -412,20 +413,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 {
                     float* dst;
                     if (EPI == EPI_GATES) dst = c0 < HC ? a.out0 + ((size_t)b * HC + c0) * plane + pix : a.out1 + ((size_t)b * HC + (c0 - HC)) * plane + pix;
-                    else dst = a.out0 + ((size_t)b * COUT + c0) * plane + pix;
+                    else dst = a.out0 + ((size_t)b * ocout + a.co_off + c0) * plane + pix;
 #pragma unroll
                     for (int c = 0; c < CG; ++c) dst[(size_t)c * plane] = res[c];
                 }
                 if (tid == 0 && gi == 0) TC_TRACE(3, ti, 2);
             };
-            static_assert(NG % 2 == 0 && C::NGW == NG / 2, "the two epilogue warp sets split the steps evenly");
             if (tid == 0) TC_TRACE(2, ti, 0);
             mbar_wait_bounded(&d_full[acc], (ti >> 1) & 1);
             tc_fence_after();
             if (C::EPI_R > 0) mbar_wait_bounded(&e_full[ti % (C::EPI_R > 0 ? C::EPI_R : 1)], (ti / (C::EPI_R > 0 ? C::EPI_R : 1)) & 1);
             if (tid == 0) TC_TRACE(2, ti, 1);
 #pragma unroll
-            for (int sI = 0; sI < C::NGW; ++sI) process(sI);
+            for (int sI = 0; sI < C::NGW; ++sI)
+                if (eset + 2 * sI < NG) process(sI);                           // steps eset, eset + 2, ... of this warp set
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -444,7 +445,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <int CA, int CB, int COUT, int EPI>
 struct TcLayer {
     // M tiles per tile: as many as the double-buffered accumulator (2 x MT x 6*Cout columns) fits into TMEM
-    static constexpr int MT = COUT <= 8 ? (EPI == EPI_CAND ? 2 : 4) : (COUT <= 16 ? 2 : 1);
+    static constexpr int MT = COUT <= 8 ? (EPI == EPI_CAND ? 2 : 4) : (COUT <= 16 ? 2 : 1);   // COUT 24, 32: 2 x 144 / 192 columns
     using G = TcGeom<MT>;
     static bool plan(ConvPlan& p, const ConvArgs& a, int B, int depthA) {
         p.args = a;

@@ -50,7 +50,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
 // in the stream is still draining; everything up to pdl_wait() (barrier init, TMEM allocation, weights into shared
 // memory - none of it produced by that kernel) overlaps its tail.  pdl_wait() returns once the preceding kernel has
 // completed and its writes are visible; nothing may be read from or written to activations before it.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

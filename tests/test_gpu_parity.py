@@ -538,7 +538,8 @@ def test_regnet_red_tensor_core_vs_oracle(C, D, h, w, up, prob):
     (32, 0, 16, 1, True, 64, 96), (64, 0, 32, 1, True, 32, 48), (64, 0, 32, 1, True, 30, 44),
     # >= 30000 pixels: the stride-1 layers switch to the tcgen05 kernel (ragged tiles: 100 = 3 x 30 + 10 columns, 106 rows)
     (8, 0, 8, 1, True, 106, 100), (16, 0, 16, 1, True, 106, 100), (32, 0, 32, 1, False, 106, 100), (16, 16, 16, 1, True, 106, 100),
-    (8, 8, 8, 1, True, 106, 100), (32, 0, 16, 1, True, 106, 100), (64, 0, 32, 1, True, 106, 100)])
+    (8, 8, 8, 1, True, 106, 100), (32, 0, 16, 1, True, 106, 100), (64, 0, 32, 1, True, 106, 100),
+    (48, 0, 48, 1, True, 106, 100)])                        # two 24-channel slices on the tensor cores
 def test_native_conv3x3_vs_torch(ca, cb, cout, stride, relu, h, w):
     """The 3x3 convolutions of FeatureNet0 / CostRegNet2D on the native kernels (FFMA: TMA and generic-tile paths;
     tcgen05 with the exact hi/lo tf32 split for large stride-1 layers) against F.conv2d in fp32 on the CPU: same math,
