@@ -433,7 +433,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int p = 0; p < 4; ++p) v[p] = sigmoid_f(v[p] + bc);
                         if (co < HC) {                  // reset gate -> r*h
                             const size_t o = ((size_t)b * HC + co) * plane + pix;
-                            const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
+                            const float4 hh = __ldcg(reinterpret_cast<const float4*>(a.hstate + o));      // L2: see pdl_wait() in tma.cuh
                             *reinterpret_cast<float4*>(a.out0 + o) = make_float4(v[0] * hh.x, v[1] * hh.y, v[2] * hh.z, v[3] * hh.w);
                         } else {
                             *reinterpret_cast<float4*>(a.out1 + ((size_t)b * HC + (co - HC)) * plane + pix) = make_float4(v[0], v[1], v[2], v[3]);
@@ -441,8 +441,8 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     } else if (EPI == EPI_CAND) {
                         const size_t o = ((size_t)b * COUT + co) * plane + pix;
                         const float bc = __ldg(a.bias + co);
-                        const float4 u = *reinterpret_cast<const float4*>(a.ugate + o);
-                        const float4 hh = *reinterpret_cast<const float4*>(a.hstate + o);
+                        const float4 u = __ldcg(reinterpret_cast<const float4*>(a.ugate + o));
+                        const float4 hh = __ldcg(reinterpret_cast<const float4*>(a.hstate + o));
                         const float uu[4] = {u.x, u.y, u.z, u.w}, hv[4] = {hh.x, hh.y, hh.z, hh.w};
 #pragma unroll
                         for (int p = 0; p < 4; ++p) v[p] = uu[p] * hv[p] + (1.f - uu[p]) * tanh_f(v[p] + bc);

@@ -1,16 +1,13 @@
-// K3 (+K4 fused): the recurrent conv-GRU encoder-decoder regulariser, swept over the D depth planes,
-// with the softmax depth regression folded into its last layer.
+// K3 + K4: the recurrent conv-GRU encoder-decoder regulariser, swept over the D depth planes, followed by the softmax
+// depth regression over its logit volume (one more kernel in the same call).
 //
 // Reference: CostRegNetRED.forward / SliceCostRegNetRED.forward (models/adamvs.py:172-195, 415-424),
 // ConvGRUCell.forward (models/module.py:24-52), ConvReLU (module.py:264-270), regression
 // (adamvs.py:306-310, 516-531; module.py:617-625).
 //
-// fp32 parity (depth 1e-4 rel / prob 1e-4 abs) rules out single-pass TF32/BF16 operands here
-// (SURVEY.md §0), and with N = 8..32 output channels a 3xTF32 tcgen05 formulation is bound by the
-// shared-memory read of the im2col A operand at ~1.3x the FFMA peak at best, so this
-// is a register-tiled FFMA direct convolution: every thread owns a 4x2 pixel patch x 8 output
-// channels (64 accumulators), input planes are staged in shared memory 8 channels at a time, weights
-// sit in shared memory as [ci][tap][co] and are read as warp-wide broadcasts.
+// fp32 parity (depth 1e-4 rel / prob 1e-4 abs) rules out single-pass TF32/BF16 operands here.  The five
+// stride-1 convolutions run on tcgen05 with an exact hi/lo tf32 operand split (conv3x3_tc.cuh) when the plane is large
+// enough, else - like conv2 and the tail always - on register-tiled FFMA kernels (conv3x3.cuh): DESIGN.md §3.
 //
 // Per depth plane (all on one stream, states/intermediates stay L2-resident):
 //   1 conv1   x1  = relu(conv3x3(F_k))                                  C  -> 8
@@ -19,7 +16,8 @@
 //   4 conv2   x2  = relu(conv3x3 stride 2 (h1))                          8  -> 16
 //   5 gates2 / 6 cand2 at half resolution                                32 -> 32 / 32 -> 16
 //   7 up1     y   = relu(convT3x3 s2 (h2) + b + h1)                      16 -> 8
-//   8 out     logit = convT3x3 s2 (y) + b  (stages 1-2) | conv3x3(y)+b (stage 3); online softmax update
+//   8 out     logit = convT3x3 s2 (y) + b  (stages 1-2) | conv3x3(y)+b (stage 3)   -> logits[:, k]      (7 + 8: one kernel)
+// After the sweep: depth, confidence = regression over logits [B,D,Ho,Wo] (regress_volume_kernel).
 #include "conv3x3.cuh"
 #include "conv3x3_tc.cuh"
 #include "regress_fused.cuh"
@@ -120,10 +118,10 @@ struct TailGeom {
 
 template <bool UP>
 __global__ void __launch_bounds__(256, 3)
-tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk_up, const float* __restrict__ up_b,
-                    const float* __restrict__ h1, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
-                    float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
-                    const float2* __restrict__ hlines, int k, int D, int h, int w) {
+tail_regress_kernel(const float* h2s, const float* __restrict__ wpk_up, const float* __restrict__ up_b,
+                    const float* h1, OutWeights ow, float* __restrict__ logits, int k, int D, int h, int w) {
+    // h2s / h1 were written by kernels this one may overlap with (programmatic dependent launch: no L1 invalidation in
+    // between, and the read-only path's contract does not hold): they are read with ld.global.cg, never __ldg / restrict.
     using G = TailGeom<UP>;
     __shared__ float sH2[16 * G::HH * G::HP];
     __shared__ float sY[8 * G::YH * G::YP];
@@ -151,7 +149,7 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
             const int cx = i % (G::QW + 1), rc = i / (G::QW + 1);
             const int ry = rc % G::HH, c = rc / G::HH;
             const int gy = qy0 + ry, gx = qx0 + cx;
-            hv[j] = (i < NE && gy >= 0 && gy < h2 && gx >= 0 && gx < w2) ? __ldg(h2s + ((size_t)b * 16 + c) * hw2 + (size_t)gy * w2 + gx) : 0.f;
+            hv[j] = (i < NE && gy >= 0 && gy < h2 && gx >= 0 && gx < w2) ? __ldcg(h2s + ((size_t)b * 16 + c) * hw2 + (size_t)gy * w2 + gx) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
@@ -175,7 +173,7 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
             const bool in = fy >= 0 && fy < h && fx >= 0 && fx < w;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                acc[q][c] = in ? __ldg(up_b + c) + __ldg(h1 + ((size_t)b * 8 + c) * hw + (size_t)fy * w + fx) : 0.f;
+                acc[q][c] = in ? __ldg(up_b + c) + __ldcg(h1 + ((size_t)b * 8 + c) * hw + (size_t)fy * w + fx) : 0.f;
         }
 #pragma unroll 4
         for (int ci = 0; ci < 16; ++ci) {
@@ -203,10 +201,10 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
     }
     __syncthreads();
 
-    // ---- phase B: output layer + online regression, two x-adjacent y pixels per thread
+    // ---- phase B: output layer, two x-adjacent y pixels per thread; logits go to the [B,D,Ho,Wo] volume
     const int ty = tid / 16, tx = (tid % 16) * 2;
     const int y0 = oy0 + ty;
-    if (y0 >= h) return;
+    if (y0 >= h || ox0 + tx >= w) return;                        // w is even: both pixels are in or out
     if (!UP) {
         float lg[2] = {sWo[72], sWo[72]};
 #pragma unroll
@@ -219,46 +217,13 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
                 lg[0] = fmaf(v0, wt[0], fmaf(v1, wt[1], fmaf(v2, wt[2], lg[0])));
                 lg[1] = fmaf(v1, wt[0], fmaf(v2, wt[1], fmaf(v3, wt[2], lg[1])));
             }
-        RegressAcc ra[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x < w) ra[e] = regress_load(st, (size_t)b * hw + y0 * w + x, k, prob_mode);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x >= w) continue;
-            const int pix = y0 * w + x;
-            if (logits_out) logits_out[((size_t)b * D + k) * hw + pix] = lg[e];
-            HypLine hl;
-            if (hlines) { const float2 t = __ldg(hlines + (size_t)b * hw + pix); hl = HypLine{t.x, t.y}; }
-            else hl = hyp_line(hs, b, pix, (int)hw, D);
-            regress_step(ra[e], lg[e], hyp_at(hl, k), prob_mode);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x < w) regress_store(st, (size_t)b * hw + y0 * w + x, ra[e], k, D, prob_mode, depth, conf);
-        }
+        *reinterpret_cast<float2*>(logits + ((size_t)b * D + k) * hw + (size_t)y0 * w + ox0 + tx) = make_float2(lg[0], lg[1]);
     } else {
-        const int Ho = 2 * h, Wo = 2 * w;
-        const size_t ohw = (size_t)Ho * Wo;
-        // 2 quads x 4 output pixels per thread: regression states first, logits and hypotheses next, stores last
-        RegressAcc ra[2][4];
-        float lg[2][4], dv[2][4];
+        const int Wo = 2 * w;
+        const size_t ohw = 4 * hw;
+        float lg[2][4];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x >= w) continue;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                ra[e][q] = regress_load(st, (size_t)b * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1), k, prob_mode);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x >= w) continue;
             float l00 = sWo[72], l01 = sWo[72], l10 = sWo[72], l11 = sWo[72];
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) {
@@ -271,39 +236,62 @@ tail_regress_kernel(const float* __restrict__ h2s, const float* __restrict__ wpk
                 l11 = fmaf(v00, wt[8], fmaf(v01, wt[6], fmaf(v10, wt[2], fmaf(v11, wt[0], l11))));
             }
             lg[e][0] = l00; lg[e][1] = l01; lg[e][2] = l10; lg[e][3] = l11;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int oy = 2 * y0 + (q >> 1), ox = 2 * x + (q & 1);
-                if (hs.mode == ADAMVS_HYP_PLANES) {
-                    dv[e][q] = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
-                } else {
-                    const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
-                    auto line_at = [&](int p) {
-                        if (hlines == nullptr) return hyp_line(hs, b, p, (int)hw, D);
-                        const float2 t = __ldg(hlines + (size_t)b * hw + p);
-                        return HypLine{t.x, t.y};
-                    };
-                    const float d00 = hyp_at(line_at(ly.i0 * w + lx.i0), k);
-                    const float d01 = hyp_at(line_at(ly.i0 * w + lx.i1), k);
-                    const float d10 = hyp_at(line_at(ly.i1 * w + lx.i0), k);
-                    const float d11 = hyp_at(line_at(ly.i1 * w + lx.i1), k);
-                    dv[e][q] = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
-                }
-                regress_step(ra[e][q], lg[e][q], dv[e][q], prob_mode);
-            }
         }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int x = ox0 + tx + e;
-            if (x >= w) continue;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const size_t o = (size_t)b * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1);
-                if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)(2 * y0 + (q >> 1)) * Wo + 2 * x + (q & 1)] = lg[e][q];
-                regress_store(st, o, ra[e][q], k, D, prob_mode, depth, conf);
-            }
-        }
+        // output rows 2*y0, 2*y0 + 1; columns 2*(ox0 + tx) .. + 3 (16-byte aligned: tx is even)
+        float* po = logits + ((size_t)b * D + k) * ohw + (size_t)(2 * y0) * Wo + 2 * (ox0 + tx);
+        *reinterpret_cast<float4*>(po) = make_float4(lg[0][0], lg[0][1], lg[1][0], lg[1][1]);
+        *reinterpret_cast<float4*>(po + Wo) = make_float4(lg[0][2], lg[0][3], lg[1][2], lg[1][3]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Regression over the logit volume, once per stage: one thread per output pixel walks the D planes (every load a
+// coalesced row segment) with the running softmax / un-shifted-exp state in registers.
+// The state used to live in global memory and was updated by the tail of every plane: 24 B read + written per output
+// pixel and plane - 29 GB per step at stage 2 (B = 16), three times the bytes of writing the logits once and reading
+// them once here, and the reason tail<UP> was the top kernel of the step (profiles/r02p_launches_bench_b16.txt).
+// Hypotheses as the reference takes them: planes, per pixel, or per pixel bilinearly upsampled x2 (align_corners =
+// False) together with the logits (module.py:622 / adamvs.py:522).
+// ------------------------------------------------------------------------------------------------
+template <bool UP>
+__global__ void __launch_bounds__(256)
+regress_volume_kernel(const float* __restrict__ logits, HypSpec hs, const float2* __restrict__ hlines, int prob_mode,
+                      float* __restrict__ depth, float* __restrict__ conf, int D, int h, int w) {
+    const int Wo = UP ? 2 * w : w, Ho = UP ? 2 * h : h;
+    const size_t ohw = (size_t)Ho * Wo;
+    const int hw = h * w;
+    const size_t o = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (o >= ohw) return;
+    const int oy = (int)(o / Wo), ox = (int)(o - (size_t)oy * Wo);
+    auto line_at = [&](int p) {
+        if (hlines == nullptr) return hyp_line(hs, b, p, hw, D);
+        const float2 t = __ldg(hlines + (size_t)b * hw + p);
+        return HypLine{t.x, t.y};
+    };
+    HypLine c00, c01, c10, c11;
+    Lerp ly{0, 0, 1.f, 0.f}, lx{0, 0, 1.f, 0.f};
+    const bool blend = UP && hs.mode == ADAMVS_HYP_PER_PIXEL;
+    if (blend) {
+        ly = lerp_index(oy, 0.5f, h); lx = lerp_index(ox, 0.5f, w);
+        c00 = line_at(ly.i0 * w + lx.i0); c01 = line_at(ly.i0 * w + lx.i1);
+        c10 = line_at(ly.i1 * w + lx.i0); c11 = line_at(ly.i1 * w + lx.i1);
+    } else {
+        c00 = hs.mode == ADAMVS_HYP_PLANES ? hyp_line(hs, b, 0, hw, D) : line_at(oy * w + ox);
+        c01 = c10 = c11 = c00;
+    }
+    const float* p = logits + (size_t)b * D * ohw + o;
+    const RegressState none{nullptr, nullptr, nullptr};
+    RegressAcc r = regress_load(none, 0, 0, prob_mode);
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+        const float lg = __ldg(p + (size_t)k * ohw);
+        float dval;
+        if (blend) dval = ly.l0 * (lx.l0 * hyp_at(c00, k) + lx.l1 * hyp_at(c01, k)) + ly.l1 * (lx.l0 * hyp_at(c10, k) + lx.l1 * hyp_at(c11, k));
+        else dval = hyp_at(c00, k);
+        regress_step(r, lg, dval, prob_mode);
+    }
+    regress_store(none, (size_t)b * ohw + o, r, D - 1, D, prob_mode, depth, conf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,11 +333,11 @@ template <int C> using TcConv1 = TcLayer<C, 0, 8, EPI_RELU>;
 
 struct Workspace {
     float *pk_conv1, *pk_gates1, *pk_cand1, *pk_conv2, *pk_gates2, *pk_cand2, *pk_up1;
-    float *x1, *h1, *rh1, *u1, *x2, *h2, *rh2, *u2, *y, *s0, *s1, *s2;
+    float *x1, *h1, *rh1, *u1, *x2, *h2, *rh2, *u2, *y, *logits;
     size_t total;
 };
 
-static Workspace carve(float* base, int B, int C, int h, int w, int out_up) {
+static Workspace carve(float* base, int B, int C, int D, int h, int w, int out_up) {
     Workspace ws;
     size_t off = 0;
     auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
@@ -364,7 +352,7 @@ static Workspace carve(float* base, int B, int C, int h, int w, int out_up) {
     ws.x1 = take(B * 8 * hw);  ws.h1 = take(B * 8 * hw);  ws.rh1 = take(B * 8 * hw);  ws.u1 = take(B * 8 * hw);
     ws.x2 = take(B * 16 * hw2); ws.h2 = take(B * 16 * hw2); ws.rh2 = take(B * 16 * hw2); ws.u2 = take(B * 16 * hw2);
     ws.y = take(B * 8 * hw);
-    ws.s0 = take(B * ohw); ws.s1 = take(B * ohw); ws.s2 = take(B * ohw);
+    ws.logits = take((size_t)B * D * ohw);                      // [B,D,Ho,Wo], unused when the caller passes logits_out
     ws.total = off;
     return ws;
 }
@@ -379,9 +367,8 @@ static cudaError_t run_conv1(const ConvArgs& a, int B, cudaStream_t st) {
 using namespace adamvs;
 
 extern "C" size_t adamvs_regnet_red_workspace_floats(int B, int C, int D, int h, int w, int out_up) {
-    (void)D;
-    if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return 0;
-    return carve(nullptr, B, C, h, w, out_up).total;
+    if (B <= 0 || C <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
+    return carve(nullptr, B, C, D, h, w, out_up).total;
 }
 
 #ifdef ADAMVS_TC_TRACE
@@ -427,10 +414,11 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
                      math_mode == ADAMVS_MATH_AUTO);
     ADAMVS_CHECK_ARG(B > 0 && B <= 65535 && D >= 2 && h > 0 && w > 0 && (h % 2) == 0 && (w % 2) == 0 && h <= 65535);
     ADAMVS_CHECK_ARG(C == 8 || C == 16 || C == 32);
+    ADAMVS_CHECK_ARG(logits_out == nullptr || reinterpret_cast<uintptr_t>(logits_out) % 16 == 0);
     ADAMVS_CHECK_ARG(prob_mode == ADAMVS_PROB_SOFTMAX || prob_mode == ADAMVS_PROB_EXP_EPS);
     ADAMVS_CHECK_ARG(hyp_mode == ADAMVS_HYP_PLANES ? hyp_ncol >= 2 : (hyp_mode == ADAMVS_HYP_PER_PIXEL && half_range));
     cudaStream_t st = (cudaStream_t)stream;
-    Workspace ws = carve(workspace, B, C, h, w, out_up);
+    Workspace ws = carve(workspace, B, C, D, h, w, out_up);
     if (ws.total > workspace_floats) return ADAMVS_ENOSPACE;
     const HypSpec hs{hyp_mode, hyp_src, hyp_ncol, half_range};
     const int h2 = h / 2, w2 = w / 2;
@@ -452,7 +440,7 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
     ADAMVS_TRY(cudaMemsetAsync(ws.h1, 0, sizeof(float) * B * 8 * hw, st));
     ADAMVS_TRY(cudaMemsetAsync(ws.h2, 0, sizeof(float) * B * 16 * hw2, st));
     const OutWeights ow{hwts->out_w, hwts->out_b};
-    const RegressState rs{ws.s0, ws.s1, ws.s2};
+    float* logits = logits_out ? logits_out : ws.logits;
     const float2* hlines = nullptr;                       // per-pixel hypothesis lines for the tail (in ws.y: y itself
     if (hyp_mode == ADAMVS_HYP_PER_PIXEL) {               // never leaves shared memory since the tail was fused)
         hyp_lines_kernel<<<(unsigned)(((size_t)B * hw + 255) / 256), 256, 0, st>>>(hs, reinterpret_cast<float2*>(ws.y), B, (int)hw, D);
@@ -538,9 +526,17 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
         // 7+8: up1 + skip + relu -> output layer -> online regression, one launch
         {
             dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
-            if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, hlines, k, D, h, w));
-            else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, hs, prob_mode, rs, depth, conf, logits_out, hlines, k, D, h, w));
+            if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, logits, k, D, h, w));
+            else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, logits, k, D, h, w));
         }
+    }
+    // K4: softmax / expectation / max over the logit volume
+    {
+        const size_t ohw = out_up ? 4 * hw : hw;
+        dim3 grid((unsigned)((ohw + 255) / 256), B, 1);
+        if (out_up) regress_volume_kernel<true><<<grid, 256, 0, st>>>(logits, hs, hlines, prob_mode, depth, conf, D, h, w);
+        else regress_volume_kernel<false><<<grid, 256, 0, st>>>(logits, hs, hlines, prob_mode, depth, conf, D, h, w);
+        ADAMVS_TRY(cudaGetLastError());
     }
     return 0;
 }

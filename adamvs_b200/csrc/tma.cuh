@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace adamvs {
 
@@ -50,6 +51,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
 // in the stream is still draining; everything up to pdl_wait() (barrier init, TMEM allocation, weights into shared
 // memory - none of it produced by that kernel) overlaps its tail.  pdl_wait() returns once the preceding kernel has
 // completed and its writes are visible; nothing may be read from or written to activations before it.
+// The SM's L1 is NOT invalidated between two overlapped kernels: data written by an earlier kernel of the chain must be
+// read through L2 (TMA, or ld.global.cg = __ldcg) - a __ldg / const __restrict__ load may return a line cached while the
+// previous plane's kernels ran (seen: stale GRU state in the tail kernel, non-deterministic logits from plane 1 on).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -58,9 +62,11 @@ template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    // ADAMVS_NO_PDL=1: plain stream order (debugging hook, read once per process)
+    static const bool no_pdl = [] { const char* e = getenv("ADAMVS_NO_PDL"); return e && *e == '1'; }();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }

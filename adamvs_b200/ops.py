@@ -244,7 +244,7 @@ def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob
     logits = torch.empty((B, D, Ho, Wo), device=volume.device, dtype=torch.float32) if want_logits else None
     keep = {k: _f32c(v, k) for k, v in weights.items()}
     st = RegnetWeights(**{k: v.data_ptr() for k, v in keep.items()})
-    with _timed("regnet_red", 7 + 7 * D):
+    with _timed("regnet_red", 9 + 7 * D):         # weight packs + hypothesis lines, 7 kernels per plane, regression
         if math is None:
             rc = lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
                                              _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),

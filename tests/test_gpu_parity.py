@@ -258,6 +258,25 @@ def test_forward_matches_reference_golden(name, cls):
         assert isinstance(leaf, torch.Tensor)
 
 
+@pytest.mark.parametrize("name,cls", [("full_d48", "stream"), ("batch2_d8", "whole")])
+def test_forward_is_bit_reproducible(name, cls):
+    """Three forwards of the same inputs give bit-identical outputs.  The kernels of the recurrent sweep overlap through
+    programmatic dependent launch; a load of the GRU state through the non-coherent L1 path (stale line from the previous
+    plane) once made planes >= 1 differ from run to run while staying inside the parity tolerance most of the time."""
+    g = load_golden(name)
+    sd, imgs, proj, dv2, dv3, meta = rebuild_case(g)
+    m = _model(cls, sd, meta["ndepths"], meta["num_depth"])
+    dv = dv3 if cls == "whole" else dv2
+    args = (imgs.to(_dev()), _to_dev(proj), dv.to(_dev()))
+    outs = []
+    for _ in range(3):
+        out = m(*args)
+        outs.append({s: (out[s]["depth"].clone(), out[s]["photometric_confidence"].clone()) for s in ("stage1", "stage2", "stage3")})
+    for o in outs[1:]:
+        for s in ("stage1", "stage2", "stage3"):
+            assert torch.equal(o[s][0], outs[0][s][0]) and torch.equal(o[s][1], outs[0][s][1]), s
+
+
 def test_intermediates_match_reference_golden():
     from adamvs_b200 import cascade
     g = load_golden("small_d8")
