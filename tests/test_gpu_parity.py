@@ -722,3 +722,35 @@ def test_config4_oblique_tile_properties(cls_name):
         hi = F.max_pool2d(src.unsqueeze(1), 5, 1, 2).squeeze(1) + hr + 1e-2
         dd = out[s]["depth"]
         assert bool(((dd >= lo) & (dd <= hi)).all()), s
+
+
+def test_predict_scene_writes_the_reference_output_files(tmp_path):
+    """Scene folder -> batches -> model -> `*_init.pfm`, `*_prob.pfm`, `*.txt`: the files hold exactly
+    what a direct forward on the same preprocessed inputs returns, in the reference's formats."""
+    import os
+    from PIL import Image
+    from adamvs_b200 import pipeline, sceneio as S, synth
+    from models.adamvs import Infer_AdaMVSNet
+    scene = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io_scene")
+    ndepths = (8, 4, 2)
+    sd = synth.fill_state_dict(synth.state_dict_shapes(ndepths[0]), 5)
+    m = Infer_AdaMVSNet(num_depth=32, ndepths=list(ndepths), depth_intervals_ratio=[4.0, 2.0, 1.0])
+    m.load_state_dict(sd)
+    m = m.to(_dev()).eval()
+    written = pipeline.predict_scene(m, scene, str(tmp_path), view_num=3, num_depth=32, max_h=64, max_w=96, batch=2, device=_dev())
+    assert len(written) == 3                                     # view 2 has no source views and is skipped
+    cams, poses = S.parse_camera_info(os.path.join(scene, "camera_info.txt")), S.parse_image_info(os.path.join(scene, "image_info.txt"))
+    paths, _ = S.parse_image_paths(os.path.join(scene, "image_path.txt"))
+    rows = S.parse_view_pairs(os.path.join(scene, "viewpair.txt"), 3)
+    for row, path in zip(rows, written):
+        images = [np.array(Image.open(os.path.join(scene, paths[i]))) for i in row[:3]]
+        imgs, proj, dv, _, blk = S.load_view_sample(row, poses, cams, images, 3, num_depth=32, max_h=64, max_w=96, device=_dev())
+        with torch.no_grad():
+            out = m(imgs[None], {k: torch.from_numpy(v)[None].to(_dev()) for k, v in proj.items()}, torch.from_numpy(dv)[None].to(_dev()))
+        depth, scale = S.read_pfm(path)
+        assert scale == 1.0 and depth.shape == (64, 96)
+        # batch of 2 vs 1: the device-side normalisation reduces in another order (1e-6 on the inputs)
+        assert rel_err(torch.from_numpy(depth.copy()), out["depth"][0].cpu()) < 1e-5
+        prob, _ = S.read_pfm(path.replace("_init.pfm", "_prob.pfm"))
+        assert abs_err(torch.from_numpy(prob.copy()), out["photometric_confidence"][0].cpu()) < 1e-5
+        assert open(path.replace("_init.pfm", ".txt")).read().startswith("extrinsic: XrightYdown, [Rcw|tcw]")
