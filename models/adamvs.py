@@ -170,8 +170,11 @@ class FeatureNet0(nn.Module):
         size = x.shape[2:]
         if (_NATIVE_CONV and not proj.training and x.is_cuda and x.dtype == torch.float32 and x.shape[3] % 4 == 0
                 and _ops.context_head_supported(x.shape[1], br_a[1].conv.out_channels, proj.out_channels)):
-            # both upsamplings, the concatenation and the 1x1 projection in one pass over x (adamvs_context_head_f32)
-            return _ops.context_head(x, br_a(x), br_b(x), proj.weight)
+            # both upsamplings, the concatenation and the 1x1 projection in one pass over x (adamvs_context_head_f32);
+            # the 8x8 average is taken from the 4x4 averages (one read of x instead of two; a mean of equal-sized means)
+            pa = br_a[0](x)
+            pb = F.avg_pool2d(pa, 2) if (br_a[0].kernel_size, br_b[0].kernel_size) == ((4, 4), (8, 8)) else br_b[0](x)
+            return _ops.context_head(x, br_a[1](pa), br_b[1](pb), proj.weight)
         a = F.interpolate(br_a(x), size=size, mode="bilinear", align_corners=False)
         c = F.interpolate(br_b(x), size=size, mode="bilinear", align_corners=False)
         return proj(torch.cat((a, c, x), 1))
