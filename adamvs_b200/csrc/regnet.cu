@@ -26,69 +26,14 @@
 namespace adamvs {
 
 // ------------------------------------------------------------------------------------------------
-// 7: y = relu(convT3x3 s2 p1 op1 (h2; 16->8) + b + h1).  One thread per half-resolution pixel: it owns
-// the 2x2 full-resolution outputs that (iy,ix) is the top-left contributor of.
+// 7+8 fused: y = relu(convT3x3 s2 p1 op1 (h2; 16->8) + b + h1) is produced per 32x16 tile (with the 1-pixel halo the
+// output layer needs, recomputed) straight into shared memory and consumed there by the output layer; y never goes to
+// global memory (saves a 32 B/px write and read per plane and one launch).  One thread per half-resolution quad owns the
+// 2x2 full-resolution pixels that (iy,ix) is the top-left contributor of (PyTorch ConvTranspose2d scatter form):
 //   out(2iy  ,2ix  ) = in(iy,ix) W11
 //   out(2iy  ,2ix+1) = in(iy,ix+1) W10 + in(iy,ix) W12
 //   out(2iy+1,2ix  ) = in(iy+1,ix) W01 + in(iy,ix) W21
 //   out(2iy+1,2ix+1) = in(iy+1,ix+1) W00 + in(iy+1,ix) W02 + in(iy,ix+1) W20 + in(iy,ix) W22
-// (PyTorch ConvTranspose2d scatter form, SURVEY.md Appendix B.)
-// ------------------------------------------------------------------------------------------------
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(128)
-upconv_add_relu_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ bias,
-                       const float* __restrict__ skip, float* __restrict__ out, int hin, int win) {
-    __shared__ float sW[CIN * 9 * COUT];
-    for (int i = threadIdx.x; i < CIN * 9 * COUT; i += blockDim.x) sW[i] = __ldg(wpk + i);
-    __syncthreads();
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int iy = blockIdx.y;
-    const int b = blockIdx.z;
-    if (ix >= win) return;
-    const size_t ip = (size_t)hin * win;
-    const int wout = 2 * win;
-    const size_t op = (size_t)4 * ip;
-    const bool hx = ix + 1 < win, hy = iy + 1 < hin;
-    float acc[4][COUT];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[q][c] = 0.f;
-    const float* pin = in + (size_t)b * CIN * ip + (size_t)iy * win + ix;
-#pragma unroll 2
-    for (int ci = 0; ci < CIN; ++ci) {
-        const float* p = pin + (size_t)ci * ip;
-        const float v00 = __ldg(p);
-        const float v01 = hx ? __ldg(p + 1) : 0.f;
-        const float v10 = hy ? __ldg(p + win) : 0.f;
-        const float v11 = (hx && hy) ? __ldg(p + win + 1) : 0.f;
-        const float* w = sW + ci * 9 * COUT;
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-            acc[0][c] += v00 * w[4 * COUT + c];
-            acc[1][c] += v01 * w[3 * COUT + c] + v00 * w[5 * COUT + c];
-            acc[2][c] += v10 * w[1 * COUT + c] + v00 * w[7 * COUT + c];
-            acc[3][c] += v11 * w[0 * COUT + c] + v10 * w[2 * COUT + c] + v01 * w[6 * COUT + c] + v00 * w[8 * COUT + c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-        const float bc = __ldg(bias + c);
-        const size_t o = ((size_t)b * COUT + c) * op + (size_t)(2 * iy) * wout + 2 * ix;
-        const float2 s0 = *reinterpret_cast<const float2*>(skip + o);
-        const float2 s1 = *reinterpret_cast<const float2*>(skip + o + wout);
-        float2 r0, r1;
-        r0.x = fmaxf(acc[0][c] + bc + s0.x, 0.f); r0.y = fmaxf(acc[1][c] + bc + s0.y, 0.f);
-        r1.x = fmaxf(acc[2][c] + bc + s1.x, 0.f); r1.y = fmaxf(acc[3][c] + bc + s1.y, 0.f);
-        *reinterpret_cast<float2*>(out + o) = r0;
-        *reinterpret_cast<float2*>(out + o + wout) = r1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// 7+8 fused: y = relu(convT(h2) + b + h1) is produced per 32x16 tile (with the 1-pixel halo the output layer needs,
-// recomputed: 1.2x of a small layer) straight into shared memory and consumed there by the output layer and the
-// online regression; y never goes to global memory (saves a 32 B/px write and read per plane and one launch).
 //   UP = false (stage 3): logit = conv3x3(y) + b on the tile            -> y halo on all four sides
 //   UP = true  (stages 1-2): logit(2y+a, 2x+b) = convT3x3 s2 (y) + b     -> y halo on the right and bottom
 // ------------------------------------------------------------------------------------------------

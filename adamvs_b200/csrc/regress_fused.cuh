@@ -125,57 +125,6 @@ out_conv_regress_kernel(const float* __restrict__ y, const float* __restrict__ y
     regress_update(st, o, acc, hyp_at(line, k), k, D, prob_mode, depth, conf);
 }
 
-// stages 1-2: logit = convT3x3 s2 (y; 8->1) + b at twice the resolution; the hypothesis of an output
-// pixel is the align_corners=False bilinear upsample of the plane's hypotheses (module.py:622).
-static __global__ void __launch_bounds__(128)
-out_upconv_regress_kernel(const float* __restrict__ y, OutWeights ow, HypSpec hs, int prob_mode, RegressState st,
-                          float* __restrict__ depth, float* __restrict__ conf, float* __restrict__ logits_out,
-                          int k, int D, int h, int w) {
-    __shared__ float sw[73];
-    stage_out_weights(ow, sw);
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int iy = blockIdx.y;
-    const int b = blockIdx.z;
-    if (ix >= w) return;
-    const size_t hw = (size_t)h * w;
-    const bool hx = ix + 1 < w, hy = iy + 1 < h;
-    float l00 = sw[72], l01 = sw[72], l10 = sw[72], l11 = sw[72];
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-        const float* p = y + ((size_t)b * 8 + ci) * hw + (size_t)iy * w + ix;
-        const float v00 = __ldg(p);
-        const float v01 = hx ? __ldg(p + 1) : 0.f;
-        const float v10 = hy ? __ldg(p + w) : 0.f;
-        const float v11 = (hx && hy) ? __ldg(p + w + 1) : 0.f;
-        const float* wt = sw + ci * 9;
-        l00 += v00 * wt[4];
-        l01 += v01 * wt[3] + v00 * wt[5];
-        l10 += v10 * wt[1] + v00 * wt[7];
-        l11 += v11 * wt[0] + v10 * wt[2] + v01 * wt[6] + v00 * wt[8];
-    }
-    const int Ho = 2 * h, Wo = 2 * w;
-    const size_t ohw = (size_t)Ho * Wo;
-    const float lg[4] = {l00, l01, l10, l11};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int oy = 2 * iy + (q >> 1), ox = 2 * ix + (q & 1);
-        float dval;
-        if (hs.mode == ADAMVS_HYP_PLANES) {
-            dval = hyp_at(hyp_line(hs, b, 0, (int)hw, D), k);
-        } else {
-            const Lerp ly = lerp_index(oy, 0.5f, h), lx = lerp_index(ox, 0.5f, w);
-            const float d00 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i0, (int)hw, D), k);
-            const float d01 = hyp_at(hyp_line(hs, b, ly.i0 * w + lx.i1, (int)hw, D), k);
-            const float d10 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i0, (int)hw, D), k);
-            const float d11 = hyp_at(hyp_line(hs, b, ly.i1 * w + lx.i1, (int)hw, D), k);
-            dval = ly.l0 * (lx.l0 * d00 + lx.l1 * d01) + ly.l1 * (lx.l0 * d10 + lx.l1 * d11);
-        }
-        const size_t o = (size_t)b * ohw + (size_t)oy * Wo + ox;
-        if (logits_out) logits_out[((size_t)b * D + k) * ohw + (size_t)oy * Wo + ox] = lg[q];
-        regress_update(st, o, lg[q], dval, k, D, prob_mode, depth, conf);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // weight packing: reference layouts -> [ci][tap][co]
 // ------------------------------------------------------------------------------------------------
