@@ -53,10 +53,11 @@ def _peaks():
         return 6650.0, 1590.0, "fallback"
 
 
-def costvolume_algorithmic_bytes(B, C, D, h, w, Vs=4, view_weights=True):
-    """every feature map read once, hypothesis source and (Ada-MVS) view weights read once,
-    the aggregated volume written once (fp32)."""
-    return 4 * B * ((1 + Vs) * C * h * w + h * w + (Vs * h * w if view_weights else 0) + C * D * h * w)
+def costvolume_algorithmic_bytes(B, C, D, h, w, Vs=4, view_weights=True, weight_px=None):
+    """every feature map read once, the hypothesis source once, the (Ada-MVS) view weights once at
+    their source resolution (`weight_px` pixels per view: the stage-1 maps), the aggregated volume written once (fp32)."""
+    wpx = (h * w if weight_px is None else weight_px) if view_weights else 0
+    return 4 * B * ((1 + Vs) * C * h * w + h * w + Vs * wpx + C * D * h * w)
 
 
 def regnet_flops(B, C, D, h, w):
@@ -327,7 +328,7 @@ def main():
         stage = name.split("/")[-1]
         if name.startswith("fused_volume/") or name.startswith("variance_volume/"):
             C, D, h, w = shapes[stage]
-            by = costvolume_algorithmic_bytes(B, C, D, h, w, view_weights=not msred)
+            by = costvolume_algorithmic_bytes(B, C, D, h, w, view_weights=not msred, weight_px=(H // 4) * (W // 4))
             entry.update({"bound": "hbm", "algorithmic_bytes": by, "achieved_GBps": by / st["ms_mean"] * 1e-6,
                           "frac_of_hbm_peak": by / st["ms_mean"] * 1e-6 / hbm_peak})
         elif name.startswith("regnet_red/") or name.startswith("regnet_msred/"):

@@ -179,3 +179,16 @@ def test_cpu_tensors_are_refused_not_emulated():
     m = A.AdaMVSNet(ndepths=[8, 4, 2]).train()
     with pytest.raises((NotImplementedError, ops.AdamvsError)):
         m(imgs, proj, torch.cat([dv, torch.full((1, 1), 5.0)], 1))
+
+
+def test_bench_accounting_matches_the_survey_definitions():
+    """bench.py's roofline numerators are SURVEY.md §8(d)'s per-unit figures: 125.4 / 175.2 / 124.2 MB of algorithmic HBM
+    bytes for the fused warp + cost volume and 17.45 / 41.11 / 38.39 GFLOP for the recurrent regulariser, per depth map."""
+    sys.path.insert(0, ROOT)
+    import bench
+    shapes = ((32, 48, 96, 192), (16, 32, 192, 384), (8, 8, 384, 768))
+    mb = [bench.costvolume_algorithmic_bytes(1, C, D, h, w, weight_px=96 * 192) / 1e6 for C, D, h, w in shapes]
+    assert [round(v, 1) for v in mb] == [125.4, 175.2, 124.2]
+    gf = [bench.regnet_flops(1, C, D, h, w) / 1e9 for C, D, h, w in shapes]
+    assert [round(v, 2) for v in gf] == [17.45, 41.11, 38.39]
+    assert all(0.9 < bench.regnet_tc_flops(1, C, D, h, w) / bench.regnet_flops(1, C, D, h, w) < 0.95 for C, D, h, w in shapes)
