@@ -2,7 +2,7 @@
 (reference models/adamvs.py:342-396 / 567-620) and of DepthNet0.forward / InferDepthNet0.forward
 (:247-312 / :433-533), re-expressed as a short sequence of C-ABI kernel calls per stage:
 
-    stage 1:  K1 pair_score -> pair U-Net (cuDNN, true fp32) -> K4 softmax_regress -> view weights
+    stage 1:  K1 pair_score -> pair U-Net (native tcgen05 / FFMA convs) -> K4 softmax_regress -> view weights
     stage s:  resize(view weights) -> K2 fused_volume -> K3 regnet_red (regression fused) -> depth, conf
 
 No host synchronisation happens inside: range scalars and relative projections are produced on the
@@ -21,8 +21,8 @@ _STAGES = ("stage1", "stage2", "stage3")
 
 
 def _true_fp32():
-    # cuDNN would otherwise run the feature / pair U-Net convolutions in TF32 (torch default), which
-    # alone breaks the 1e-4 probability tolerance.
+    # The few layers still on torch (average pools + 1x1 convs of the pooled context maps; everything under train())
+    # must not run in cuDNN's default TF32, which alone breaks the 1e-4 probability tolerance.
     return torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                       deterministic=False, allow_tf32=False)
 
@@ -62,7 +62,7 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
     imgs = imgs.float()
     depth_values = depth_values.float().contiguous()
     ops.set_tag("all")
-    with ops.timed("featurenet_cudnn", 0):
+    with ops.timed("featurenet", 0):
         feats = extract_features(net, imgs)
     relproj, half = ops.cascade_prepare(
         [proj_matrices[k] for k in _STAGES], depth_values,
@@ -81,14 +81,17 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
         _, _, C, h, w = feat.shape
         D = ndepths[i]
         if depth is None:
-            hyp = ops.Hyp(ops.HYP_PLANES, depth_values)
+            # first-stage planes run from depth_values[:,0] to [:,-1] (predict class, adamvs.py:569-570) or [:,-2]
+            # (train/test class, :344-345: the last column is the interval) whatever the number of columns
+            plane_range = torch.stack((depth_values[:, 0], depth_values[:, -1 if stream_conv else -2]), 1).contiguous()
+            hyp = ops.Hyp(ops.HYP_PLANES, plane_range)
         else:
             assert tuple(depth.shape) == (B, h, w), (depth.shape, (B, h, w))
             hyp = ops.Hyp(ops.HYP_PER_PIXEL, depth, half[i:i + 1])
         pair_depths: List[torch.Tensor] = []
         if stage1_w is None:
             score = ops.pair_score(feat, relproj[i], hyp, D)                     # [B,Vs,D,h,w]
-            with ops.timed("pair_unet_cudnn", 0), _true_fp32():
+            with ops.timed("pair_unet", 0), _true_fp32():
                 pair_logits = net.DepthNet[i].reg(score.reshape(B * (V - 1), D, h, w))
             pd, pc = ops.softmax_regress(pair_logits, hyp, ops.PROB_SOFTMAX, n_per_batch=V - 1)
             stage1_w = pc.reshape(B, V - 1, h, w)

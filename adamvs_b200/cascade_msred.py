@@ -52,7 +52,7 @@ def _forward(net, imgs, proj_matrices, depth_values, capture):
     imgs = imgs.float()
     depth_values = depth_values.float().contiguous()
     ops.set_tag("all")
-    with ops.timed("featurenet_cudnn", 0):
+    with ops.timed("featurenet", 0):
         feats = _features(net, imgs)
     relproj, half = ops.cascade_prepare(
         [proj_matrices[k] for k in _STAGES], depth_values,

@@ -157,6 +157,36 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _guard(t: torch.Tensor):
+    """The C library launches on the CURRENT device (it never calls cudaSetDevice; its SM-count / attribute caches are
+    per device): make the tensors' device current for the duration of the call, so that
+    predict_scene(device=cuda:1) from a process whose current device is cuda:0 launches where the pointers live.
+    _stream() is evaluated inside, i.e. it is that device's current stream."""
+    if not t.is_cuda:
+        raise AdamvsError("adamvs_b200 runs on CUDA tensors only (no CPU fallback)")
+    return torch.cuda.device(t.device)
+
+
+def _same_device(*ts):
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise AdamvsError(f"all tensors of one call must live on one device, got {dev} and {t.device}")
+
+
+_default_math = None    # None = the library default (exact split); bench.py --math tf32 sets MATH_TC_TF32
+
+
+def set_default_math(mode):
+    """Arithmetic of regnet_red when the caller does not pass `math` (None = library default, the fp32-parity path)."""
+    global _default_math
+    _default_math = mode
+
+
 class Hyp:
     """Depth-hypothesis source for one stage (reference get_depth_range_samples, module.py:646-663)."""
 
@@ -176,11 +206,12 @@ def cascade_prepare(proj: Sequence[torch.Tensor], depth_values: torch.Tensor, in
     p1, p2, p3 = (_f32c(p, "proj") for p in proj)
     dv = _f32c(depth_values, "depth_values")
     B, V = p1.shape[0], p1.shape[1]
+    _same_device(p1, p2, p3, dv)
     relproj = torch.empty((3, B, V - 1, 12), device=p1.device, dtype=torch.float32)
     half = torch.empty((3,), device=p1.device, dtype=torch.float32)
     nd = (ctypes.c_int * 3)(*[int(x) for x in ndepths])
     rt = (ctypes.c_double * 3)(*[float(x) for x in ratios])
-    with _timed("cascade_prepare", 2):
+    with _guard(p1), _timed("cascade_prepare", 2):
         _check(lib().adamvs_cascade_prepare(_p(p1), _p(p2), _p(p3), _p(dv), dv.shape[1], B, V, interval_mode,
                                             int(num_depth), nd, rt, _p(relproj), _p(half), _stream()), "cascade_prepare")
     return relproj, half
@@ -190,7 +221,7 @@ def pair_score(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, D: int) -> t
     feat = _f32c(feat, "feat")
     B, V, C, h, w = feat.shape
     out = torch.empty((B, V - 1, D, h, w), device=feat.device, dtype=torch.float32)
-    with _timed("pair_score", 1):
+    with _guard(feat), _timed("pair_score", 1):
         _check(lib().adamvs_pair_score_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
                                            B, V, C, D, h, w, _stream()), "pair_score")
     return out
@@ -205,7 +236,7 @@ def resize_bilinear(x: torch.Tensor, ho: int, wo: int) -> torch.Tensor:
     for s in lead:
         n *= int(s)
     out = torch.empty((*lead, ho, wo), device=x.device, dtype=torch.float32)
-    with _timed("resize_bilinear", 1):
+    with _guard(x), _timed("resize_bilinear", 1):
         _check(lib().adamvs_resize_bilinear_f32(_p(x), _p(out), n, hi, wi, ho, wo, _stream()), "resize_bilinear")
     return out
 
@@ -216,9 +247,10 @@ def fused_volume(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, weights: t
     B, V, C, h, w = feat.shape
     weights = _f32c(weights, "weights")
     assert tuple(weights.shape) == (B, V - 1, h, w), (weights.shape, (B, V - 1, h, w))
+    _same_device(feat, relproj, hyp.src, weights, out)
     if out is None:
         out = torch.empty((B, C, D, h, w), device=feat.device, dtype=torch.float32)
-    with _timed("fused_volume", 1):
+    with _guard(feat), _timed("fused_volume", 1):
         _check(lib().adamvs_fused_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(weights), eps_mode,
                                              _p(out), B, V, C, D, h, w, _stream()), "fused_volume")
     return out
@@ -244,7 +276,9 @@ def regnet_red(volume: torch.Tensor, weights: dict, hyp: Hyp, out_up: bool, prob
     logits = torch.empty((B, D, Ho, Wo), device=volume.device, dtype=torch.float32) if want_logits else None
     keep = {k: _f32c(v, k) for k, v in weights.items()}
     st = RegnetWeights(**{k: v.data_ptr() for k, v in keep.items()})
-    with _timed("regnet_red", 9 + 7 * D):         # weight packs + hypothesis lines, 7 kernels per plane, regression
+    with _guard(volume), _timed("regnet_red", 9 + 7 * D):         # weight packs + hypothesis lines, 7 kernels per plane, regression
+        if math is None:
+            math = _default_math
         if math is None:
             rc = lib().adamvs_regnet_red_f32(_p(volume), ctypes.byref(st), *hyp.args(), int(out_up), prob_mode,
                                              _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
@@ -263,7 +297,7 @@ def softmax_regress(logits: torch.Tensor, hyp: Hyp, prob_mode: int, n_per_batch:
     N, D, h, w = logits.shape
     depth = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
     conf = torch.empty((N, h, w), device=logits.device, dtype=torch.float32)
-    with _timed("softmax_regress", 1):
+    with _guard(logits), _timed("softmax_regress", 1):
         _check(lib().adamvs_softmax_regress_f32(_p(logits), *hyp.args(), prob_mode, _p(depth), _p(conf),
                                                 N, n_per_batch, D, h, w, _stream()), "softmax_regress")
     return depth, conf
@@ -277,7 +311,7 @@ def variance_volume(feat: torch.Tensor, relproj: torch.Tensor, hyp: Hyp, D: int,
     B, V, C, h, w = feat.shape
     if out is None:
         out = torch.empty((B, C, D, h, w), device=feat.device, dtype=torch.float32)
-    with _timed("variance_volume", 1):
+    with _guard(feat), _timed("variance_volume", 1):
         _check(lib().adamvs_variance_volume_f32(_p(feat), _p(_f32c(relproj, "relproj")), *hyp.args(), _p(out),
                                                 B, V, C, D, h, w, _stream()), "variance_volume")
     return out
@@ -307,7 +341,7 @@ def regnet_msred(volume: torch.Tensor, weights: dict, hyp: Hyp, prob_mode: int,
             t = _f32c(v, name)
             keep.append(t)
             setattr(st, name, t.data_ptr())
-    with _timed("regnet_msred", 11 + 25 * D):
+    with _guard(volume), _timed("regnet_msred", 11 + 25 * D):
         _check(lib().adamvs_regnet_msred_f32(_p(volume), ctypes.byref(st), *hyp.args(), prob_mode,
                                              _p(workspace), workspace.numel(), _p(depth), _p(conf), _p(logits),
                                              B, C, D, h, w, _stream()), "regnet_msred")
@@ -335,7 +369,7 @@ def conv3x3(xa: torch.Tensor, xb: Optional[torch.Tensor], wpk: torch.Tensor, bia
         CB = xb.shape[1]
     COUT = wpk.shape[2]
     out = torch.empty((N, COUT, h // stride, w // stride), device=xa.device, dtype=torch.float32)
-    with _timed("conv3x3", 1):
+    with _guard(xa), _timed("conv3x3", 1):
         _check(lib().adamvs_conv3x3_f32(_p(xa), CA, _p(xb), CB, _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu),
                                         int(stride), _p(out), N, COUT, h, w, _stream()), "conv3x3")
     return out
@@ -356,7 +390,7 @@ def context_head(x: torch.Tensor, ctx_a: torch.Tensor, ctx_c: torch.Tensor, weig
     if ctx_c.shape[1] != CCTX or wt.shape[1] != 2 * CCTX + CX or ctx_a.shape[0] != N or ctx_c.shape[0] != N:
         raise ValueError("context_head: inconsistent shapes")
     out = torch.empty((N, COUT, h, w), device=x.device, dtype=torch.float32)
-    with _timed("context_head", 1):
+    with _guard(x), _timed("context_head", 1):
         _check(lib().adamvs_context_head_f32(_p(x), _p(ctx_a), _p(ctx_c), _p(wt), _p(out), N, CX, CCTX, COUT, h, w,
                                              ctx_a.shape[2], ctx_a.shape[3], ctx_c.shape[2], ctx_c.shape[3], _stream()),
                "context_head")
@@ -378,7 +412,7 @@ def deconv3x3(x: torch.Tensor, wpk: torch.Tensor, bias: torch.Tensor, relu: bool
     N, CIN, h, w = x.shape
     COUT = wpk.shape[2]
     out = torch.empty((N, COUT, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
-    with _timed("deconv3x3", 1):
+    with _guard(x), _timed("deconv3x3", 1):
         _check(lib().adamvs_deconv3x3_f32(_p(x), _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu), _p(out),
                                           N, CIN, COUT, h, w, _stream()), "deconv3x3")
     return out

@@ -79,6 +79,9 @@ def predict_scene(model, scene_dir: str, out_dir: str, view_num: int = 5, num_de
             pyr = S.projection_pyramid(np.stack([S.projection_matrix(b) for b in blks]))
             for k in projs:
                 projs[k].append(torch.from_numpy(pyr[k]))
+            if any(c.shape != crops[0].shape for c in crops) or (raw and crops[0].shape != raw[0].shape[1:]):
+                raise ValueError("predict_scene: every cropped view of a batch must have one size (got "
+                                 f"{sorted({tuple(c.shape) for c in crops})}); use batch=1 for scenes with mixed image sizes")
             raw.append(torch.stack(crops))
             dvs.append(torch.tensor([blks[0][1][3][0], blks[0][1][3][3]], dtype=torch.float32))
             meta.append((poses[row[0]].name, blks[0], paths[row[0]]))
@@ -86,29 +89,31 @@ def predict_scene(model, scene_dir: str, out_dir: str, view_num: int = 5, num_de
         return (pin(torch.stack(raw)), {k: pin(torch.stack(v)) for k, v in projs.items()}, pin(torch.stack(dvs))), meta
 
     written = []
-    pre = InputPrefetcher(device)
     chunks = [rows[i:i + batch] for i in range(0, len(rows), batch)]
     if not chunks:
         return written
-    nxt, nxt_meta = host_batch(chunks[0])
-    pre.stage(nxt)
-    model = model.to(device).eval()
-    for ci in range(len(chunks)):
-        raw, proj, dv = pre.take()
-        meta = nxt_meta
-        if ci + 1 < len(chunks):
-            nxt, nxt_meta = host_batch(chunks[ci + 1])
-            pre.stage(nxt)
-        with torch.no_grad():
-            out = model(S.center_images(raw), proj, dv)
-        depth = out["depth"].cpu().numpy()
-        prob = out["photometric_confidence"].cpu().numpy()
-        for j, (name, blk, ref_path) in enumerate(meta):
-            stem = os.path.splitext(os.path.basename(name))[0]
-            view_dir = os.path.join(out_dir, os.path.dirname(name).split("/")[-1])
-            os.makedirs(view_dir, exist_ok=True)
-            S.write_pfm(os.path.join(view_dir, stem + "_init.pfm"), np.ascontiguousarray(depth[j], dtype=np.float32))
-            S.write_pfm(os.path.join(view_dir, stem + "_prob.pfm"), np.ascontiguousarray(prob[j], dtype=np.float32))
-            S.write_cam_txt(os.path.join(view_dir, stem + ".txt"), blk, ref_path)
-            written.append(os.path.join(view_dir, stem + "_init.pfm"))
+    with torch.cuda.device(device):                   # the C library launches on the current device (ops._guard)
+        pre = InputPrefetcher(device)
+        nxt, nxt_meta = host_batch(chunks[0])
+        pre.stage(nxt)
+        model = model.to(device).eval()
+        for ci in range(len(chunks)):
+            raw, proj, dv = pre.take()
+            meta = nxt_meta
+            with torch.no_grad():
+                out = model(S.center_images(raw), proj, dv)       # asynchronous: the kernels are only enqueued here
+            if ci + 1 < len(chunks):
+                # decode / crop / pin the next batch on the host WHILE the GPU computes this one, then start its copy
+                nxt, nxt_meta = host_batch(chunks[ci + 1])
+                pre.stage(nxt)
+            depth = out["depth"].cpu().numpy()                    # first host sync of the iteration
+            prob = out["photometric_confidence"].cpu().numpy()
+            for j, (name, blk, ref_path) in enumerate(meta):
+                stem = os.path.splitext(os.path.basename(name))[0]
+                view_dir = os.path.join(out_dir, os.path.dirname(name).split("/")[-1])
+                os.makedirs(view_dir, exist_ok=True)
+                S.write_pfm(os.path.join(view_dir, stem + "_init.pfm"), np.ascontiguousarray(depth[j], dtype=np.float32))
+                S.write_pfm(os.path.join(view_dir, stem + "_prob.pfm"), np.ascontiguousarray(prob[j], dtype=np.float32))
+                S.write_cam_txt(os.path.join(view_dir, stem + ".txt"), blk, ref_path)
+                written.append(os.path.join(view_dir, stem + "_init.pfm"))
     return written

@@ -13,8 +13,17 @@ Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e``
 through the public forward() with pinned-host inputs and a device->host read of the results inside
 the timed region.  ``roofline`` is measured live with CUDA events around the fused cost-volume kernel
 (K2, HBM-bound — the kernel BASELINE.json's metric names); ``kernels`` lists every C-ABI kernel's share
-of the step and its own bound.  ``cpu_baseline`` / ``--impl reference`` time the oracle's CPU port of
-the reference (the reference itself is Python and does not travel to the GPU box).
+of the step and its own bound.  ``cpu_baseline`` / ``--impl reference`` time the UNMODIFIED reference modules
+(``baseline/_ref``, a git-ignored copy of /root/reference made by ``baseline/install_ref.py``; ``kind: "reference"``)
+on the box's host cores, falling back to the oracle's CPU port (``kind: "port"``) only when that copy is absent.
+``library_bar`` is the same unmodified reference run eagerly on the SAME B200 (true fp32, and PyTorch's TF32
+defaults + cudnn.benchmark as predict_whu.py:20 sets them) — the GPU library path this build is to beat.
+
+    --workload config1   configs[1]/[2]: 5-view 768x384, ndepths 48/32/8 (default, the headline)
+    --workload config4   configs[3]: 5-view 1536x1536 oblique tile, ndepths 96/32/8 (memory-bound cost-volume stress)
+    --model msrednet     configs[4]: MS-REDNet, ndepths 128/32/8
+    --math fp32|tf32     K3 arithmetic: fp32 = exact hi/lo tf32 split (default, the parity path); tf32 = single-pass
+                         tf32 activations (reported separately, own tolerance: depth 5e-3 rel / prob 3e-2 abs)
 """
 from __future__ import annotations
 
@@ -30,18 +39,46 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W, V = 384, 768, 5
-NDEPTHS = (48, 32, 8)
+V = 5
 RATIOS = (4.0, 2.0, 1.0)
-NUM_DEPTH = 192
-MS_NDEPTHS = (128, 32, 8)          # BASELINE config 5: MS-REDNet, D = 128 planes at the first stage
-MS_NUM_DEPTH = 512
 METRIC = "depth maps/sec, 5-view 768x384"
 UNIT = "depth_maps/s"
-MS_WORKLOAD = ("configs[4]: MS-REDNet (Infer_CascadeREDNet) 5-view 768x384, ndepths 128/32/8, fp32, random-init weights; "
-               "reference views sharded over ranks")
-WORKLOAD = ("configs[1]: Ada-MVS 5-view (1 ref + 4 src) 768x384 cascade inference, fp32, random-init weights; "
-            "reference views are independent and are sharded over ranks (configs[2])")
+
+
+class Workload:
+    """One BASELINE.json config: image size, hypothesis counts, model class, default batch per GPU."""
+
+    def __init__(self, key, H, W, ndepths, num_depth, model, batch, text):
+        self.key, self.H, self.W, self.ndepths, self.num_depth = key, H, W, tuple(ndepths), num_depth
+        self.model, self.batch, self.text = model, batch, text
+
+    @property
+    def msred(self):
+        return self.model == "msrednet"
+
+    @property
+    def cls(self):
+        return "Infer_CascadeREDNet" if self.msred else "Infer_AdaMVSNet"
+
+    def config(self, B, math="fp32"):
+        """The `config` object of the JSON line; identical for the `ours` and the `reference` arm."""
+        return {"workload": self.text, "class": self.cls, "ndepths": list(self.ndepths), "num_depth": self.num_depth,
+                "views": V, "height": self.H, "width": self.W, "batch_per_gpu_per_step": B, "math": math,
+                "weights": "seeded random init, calibrated (SURVEY A.6)",
+                "l2": "3 distinct input batches cycled; >1 GB of cost volume written/read per step (>> 126 MB L2)"}
+
+
+WORKLOADS = {
+    "config1": Workload("config1", 384, 768, (48, 32, 8), 192, "adamvs", 32,
+                        "configs[1]: Ada-MVS 5-view (1 ref + 4 src) 768x384 cascade inference, fp32, random-init weights; "
+                        "reference views are independent and are sharded over ranks (configs[2])"),
+    "config4": Workload("config4", 1536, 1536, (96, 32, 8), 192, "adamvs", 4,
+                        "configs[3]: Ada-MVS 5-view full-res oblique tile 1536x1536, widened first stage (ndepths 96/32/8), "
+                        "fp32, random-init weights; memory-bound cost-volume stress"),
+    "msrednet": Workload("msrednet", 384, 768, (128, 32, 8), 512, "msrednet", 32,
+                         "configs[4]: MS-REDNet (Infer_CascadeREDNet) 5-view 768x384, ndepths 128/32/8, fp32, random-init "
+                         "weights; reference views sharded over ranks"),
+}
 
 
 def _peaks():
@@ -131,24 +168,73 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_maps_per_s(n_maps=3, warmup=1, model="adamvs"):
-    """The oracle's CPU port of the predict class' forward, all host threads, B=1 (reference's own batch size)."""
+def _build_case(wl, seed=0, gain=None):
+    """Seeded inputs (B=1) and the seeded, calibrated state_dict of the workload's predict class (CPU tensors)."""
     import torch
     from adamvs_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
-    imgs, proj, dv = synth.make_sample(1, H, W, V, seed=0)
-    if model == "adamvs":
-        from oracle import adamvs_oracle as O
-        sd = synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 0)
-        f = O.feature_net(sd, imgs[:, 0])
-        sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
-        run = lambda: O.infer_adamvs_forward(sd, imgs, proj, dv, num_depth=NUM_DEPTH, ndepths=NDEPTHS, ratios=RATIOS)
-    else:
-        from oracle import msrednet_oracle as MO
+    imgs, proj, dv = synth.make_sample(1, wl.H, wl.W, V, seed=seed)
+    return imgs, proj, dv
+
+
+def _reference_model(wl, sd):
+    """The UNMODIFIED reference's predict class (baseline/_ref) with `sd` loaded; None when it is not installed."""
+    import contextlib
+    import io
+    from baseline import refload
+    if refload.reference_root() is None:
+        return None
+    with contextlib.redirect_stdout(io.StringIO()):
+        if wl.msred:
+            ref = refload.load("msrednet")
+            m = ref.Infer_CascadeREDNet(num_depth=wl.num_depth, ndepths=list(wl.ndepths), depth_interals_ratio=list(RATIOS))
+        else:
+            ref = refload.load("adamvs")
+            m = ref.Infer_AdaMVSNet(num_depth=wl.num_depth, ndepths=list(wl.ndepths), depth_intervals_ratio=list(RATIOS))
+    m.load_state_dict(sd)
+    return m.eval()
+
+
+def _calibrated_state_dict(wl, imgs, feature_fn):
+    from adamvs_b200 import synth
+    if wl.msred:
         sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 0)
-        f = MO.feature_net(sd, imgs[:, 0])
-        sd = synth.calibrate_msred_state_dict(sd, {k: float(f[k].std()) for k in f}, 4.0)
-        run = lambda: MO.infer_cascade_rednet_forward(sd, imgs, proj, dv, num_depth=MS_NUM_DEPTH, ndepths=MS_NDEPTHS, ratios=RATIOS)
+        f = feature_fn(sd, imgs[:, 0])
+        return synth.calibrate_msred_state_dict(sd, {k: float(f[k].std()) for k in f}, 4.0)
+    sd = synth.fill_state_dict(synth.state_dict_shapes(wl.ndepths[0]), 0)
+    f = feature_fn(sd, imgs[:, 0])
+    return synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 60.0)
+
+
+def cpu_reference_maps_per_s(wl, n_maps=3, warmup=1):
+    """The reference's CPU path on all host threads, B=1 (the reference's own batch size): the unmodified reference
+    modules from baseline/_ref when installed (kind "reference"), else the oracle's torch-CPU port (kind "port")."""
+    import warnings
+    import torch
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs, proj, dv = _build_case(wl)
+    if wl.msred:
+        from oracle import msrednet_oracle as O
+    else:
+        from oracle import adamvs_oracle as O
+    sd = _calibrated_state_dict(wl, imgs, O.feature_net)
+    kind = "port"
+    try:
+        model = _reference_model(wl, sd)
+    except Exception as e:                                  # a broken copy must not take the bench line down
+        print(f"bench: reference import failed ({e!r}); timing the oracle port", file=sys.stderr)
+        model = None
+    if model is not None:
+        from baseline import refload
+        kind = "reference"
+
+        def run():
+            with refload.cpu_cuda_shim(), torch.no_grad():
+                model(imgs, proj, dv)
+    elif wl.msred:
+        run = lambda: O.infer_cascade_rednet_forward(sd, imgs, proj, dv, num_depth=wl.num_depth, ndepths=wl.ndepths, ratios=RATIOS)
+    else:
+        run = lambda: O.infer_adamvs_forward(sd, imgs, proj, dv, num_depth=wl.num_depth, ndepths=wl.ndepths, ratios=RATIOS)
     times = []
     for i in range(warmup + n_maps):
         t0 = time.perf_counter()
@@ -156,28 +242,75 @@ def cpu_reference_maps_per_s(n_maps=3, warmup=1, model="adamvs"):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return 1.0 / statistics.median(times), torch.get_num_threads(), times
+    return 1.0 / statistics.median(times), torch.get_num_threads(), times, kind
 
 
-def run_reference(args):
+def library_bar(wl, model_ours, dev, n_maps=3):
+    """The unmodified reference run eagerly on this GPU (B=1, its own batch size), same seeded weights and inputs:
+    true fp32 (also a full-size parity check of our forward against it) and PyTorch's defaults as predict_whu.py:20
+    runs (cuDNN TF32 allowed, cudnn.benchmark=True).  Baseline only: none of our kernels are on this path."""
+    import torch
+    imgs, proj, dv = _build_case(wl)
+    sd = {k: v.detach().cpu() for k, v in model_ours.state_dict().items()}
+    try:
+        ref = _reference_model(wl, sd)
+    except Exception as e:
+        return {"unavailable": f"reference import failed: {e!r}"}
+    if ref is None:
+        return {"unavailable": "baseline/_ref absent (run baseline/install_ref.py in the build container)"}
+    ref = ref.to(dev)
+    di, dp, dd = imgs.to(dev), {k: v.to(dev) for k, v in proj.items()}, dv.to(dev)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {"batch": 1, "unit": UNIT, "what": "reference Infer_* forward, eager PyTorch CUDA on this GPU, inputs resident"}
+    keep = {}
+    try:
+        for tag, tf32, bench in (("fp32", False, False), ("tf32_default_cudnn_benchmark", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = bench
+            times = []
+            with torch.no_grad():
+                for i in range(2 + n_maps):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    o = ref(di, dp, dd)
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        times.append(time.perf_counter() - t0)
+            keep[tag] = o
+            out[tag] = {"value": 1.0 / statistics.median(times), "ms_per_map": 1e3 * statistics.median(times), "maps": n_maps}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    # full-size parity of our forward against the true-fp32 reference on this GPU (same weights, same inputs)
+    with torch.no_grad():
+        mine = model_ours(di, dp, dd)
+    want = keep["fp32"]
+    par = {}
+    for s in ("stage1", "stage2", "stage3"):
+        d0, d1 = want[s]["depth"].double(), mine[s]["depth"].double()
+        p0, p1 = want[s]["photometric_confidence"].double(), mine[s]["photometric_confidence"].double()
+        par[s] = {"depth_rel_max": float(((d1 - d0).abs() / d0.abs()).max()), "prob_abs_max": float((p1 - p0).abs().max())}
+    out["parity_ours_vs_reference_fp32"] = par
+    return out
+
+
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    steps = min(steps, 10)                                   # bounded sample: one depth map per step
-    mps, cores, times = cpu_reference_maps_per_s(n_maps=steps, warmup=min(warm, 2), model=args.model)
+    B = max(1, args.batch or wl.batch)
+    mps, cores, times, kind = cpu_reference_maps_per_s(wl, n_maps=steps, warmup=warm)
+    sample = (f"{steps} steps of ONE depth map each (B=1, the reference's own batch size; same {V}-view {wl.W}x{wl.H} "
+              f"workload, weights and inputs as the GPU arm), median, after {warm} warm-up; "
+              + ("unmodified reference modules from baseline/_ref, Tensor.cuda shimmed to identity" if kind == "reference"
+                 else "oracle torch-CPU port (baseline/_ref absent)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warm, 2), "ms_per_step": 1e3 / mps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 / mps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.model == "adamvs" else MS_WORKLOAD,
-                   "class": "Infer_AdaMVSNet" if args.model == "adamvs" else "Infer_CascadeREDNet",
-                   "ndepths": list(NDEPTHS if args.model == "adamvs" else MS_NDEPTHS),
-                   "num_depth": NUM_DEPTH if args.model == "adamvs" else MS_NUM_DEPTH,
-                   "views": V, "arm": "oracle torch-CPU port of the reference's PyTorch path, B=1 per step (the "
-                                      "reference's own batch size), all host threads"},
-        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} depth maps (1 per step), median, after {min(warm, 2)} warm-up"},
+        "config": wl.config(B, args.math),
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -189,21 +322,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("ADAMVS_BENCH_BATCH", "32")),
-                    help="reference views per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("ADAMVS_BENCH_BATCH", "0")),
+                    help="reference views per GPU per step (default: the workload's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--model", default="adamvs", choices=["adamvs", "msrednet"],
-                    help="adamvs = the headline (configs[1]/[2]); msrednet = BASELINE config 5")
+                    help="adamvs = the headline (configs[1]/[2]); msrednet = BASELINE configs[4]")
+    ap.add_argument("--workload", default="config1", choices=["config1", "config4"],
+                    help="config1 = configs[1]/[2] 768x384 (headline); config4 = configs[3] 1536x1536, ndepths 96/32/8")
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
+                    help="K3 arithmetic: fp32 (exact split, parity path) | tf32 (single-pass activations, reported separately)")
     args = ap.parse_args()
+    wl = WORKLOADS["msrednet" if args.model == "msrednet" else args.workload]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, wl)
 
     import torch
     import torch.distributed as dist
     from adamvs_b200 import ops, synth
-    from models.adamvs import Infer_AdaMVSNet
 
+    H, W = wl.H, wl.W
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,33 +354,37 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     min_warm = 1 if os.environ.get("ADAMVS_BENCH_PROFILING") else 3      # profiler passes only; never a bench value
-    steps, warm, B = max(1, args.steps), max(min_warm, args.warmup), max(1, args.batch)
+    steps, warm, B = max(1, args.steps), max(min_warm, args.warmup), max(1, args.batch or wl.batch)
+    if args.math == "tf32":
+        ops.set_default_math(ops.MATH_TC_TF32)
 
     # ---- model: seeded random-init weights, calibrated so that probabilities are not uniform
-    msred = args.model == "msrednet"
+    msred = wl.msred
     with open(os.devnull, "w") as devnull:
         stdout, sys.stdout = sys.stdout, devnull
         try:
             if msred:
                 from models.msrednet import Infer_CascadeREDNet
-                model = Infer_CascadeREDNet(num_depth=MS_NUM_DEPTH, ndepths=list(MS_NDEPTHS), depth_interals_ratio=list(RATIOS))
+                model = Infer_CascadeREDNet(num_depth=wl.num_depth, ndepths=list(wl.ndepths), depth_interals_ratio=list(RATIOS))
             else:
-                model = Infer_AdaMVSNet(num_depth=NUM_DEPTH, ndepths=list(NDEPTHS), depth_intervals_ratio=list(RATIOS))
+                from models.adamvs import Infer_AdaMVSNet
+                model = Infer_AdaMVSNet(num_depth=wl.num_depth, ndepths=list(wl.ndepths), depth_intervals_ratio=list(RATIOS))
         finally:
             sys.stdout = stdout
-    sd = synth.fill_state_dict(synth.msred_state_dict_shapes() if msred else synth.state_dict_shapes(NDEPTHS[0]), 0)
-    model.load_state_dict(sd)
     model = model.to(dev).eval()
+
+    def feat_on_gpu(sd, img):
+        model.load_state_dict(sd)
+        with torch.no_grad():
+            return model.feature(img.to(dev))
+    # calibration on the same B=1 seed-0 sample the reference arm uses => both arms run identical weights
+    sd = _calibrated_state_dict(wl, _build_case(wl)[0], feat_on_gpu)
+    model.load_state_dict(sd)
     NSETS = 3                                                # distinct input batches, cycled (not L2-hot)
     host = []
     for s in range(NSETS):
         imgs, proj, dv = synth.make_sample(B, H, W, V, seed=1 + rank * NSETS + s)
         host.append((imgs.pin_memory(), {k: v.pin_memory() for k, v in proj.items()}, dv.pin_memory()))
-    with torch.no_grad():
-        f = model.feature(host[0][0][:1, 0].to(dev))
-    fstd = {k: float(f[k].std()) for k in f}
-    sd = synth.calibrate_msred_state_dict(sd, fstd, 4.0) if msred else synth.calibrate_state_dict(sd, fstd, 60.0)
-    model.load_state_dict(sd)
     resident = [(i.to(dev), {k: v.to(dev) for k, v in p.items()}, d.to(dev)) for i, p, d in host]
 
     def barrier():
@@ -315,12 +458,13 @@ def main():
     # ---- per-kernel accounting (rank 0): mean device time per launch from the CUDA events
     hbm_peak, tensor_peak, peak_src = _peaks()
     ffma_peak = 56.3                                         # TFLOP/s, tools/ffma_probe.cu on this pool (profiles/r01_ffma_probe.txt)
+    tf32_peak, tf32_src = _tf32_peak(tensor_peak)
     per_kernel = {}
     for name, evs in timing.items():
         ms = [a.elapsed_time(b) for a, b in evs]
         per_kernel[name] = {"launches": len(ms), "ms_mean": sum(ms) / len(ms), "ms_total": sum(ms)}
     step_ms = ms_total / steps
-    nd = MS_NDEPTHS if msred else NDEPTHS
+    nd = wl.ndepths
     shapes = {"stage1": (32, nd[0], H // 4, W // 4), "stage2": (16, nd[1], H // 2, W // 2), "stage3": (8, nd[2], H, W)}
     kernels = {}
     for name, st in per_kernel.items():
@@ -340,13 +484,16 @@ def main():
             if msred:
                 entry["bound"] = "fp32 FFMA (GroupNorm conv-GRU on the FFMA kernels)"
             else:
-                # fp32 accuracy on kind::tf32: (A_hi + A_lo)(W_hi + W_lo) = 4 tf32 products per fp32 product
+                # fp32 accuracy on kind::tf32: (A_hi + A_lo)(W_hi + W_lo) = 4 tf32 products per fp32 product;
+                # --math tf32 drops the A_lo pass: 2 per product
+                passes = 2 if args.math == "tf32" else 4
                 tcf = regnet_tc_flops(B, C, D, h, w)
-                entry.update({"bound": "tensor (tcgen05 kind::tf32, exact hi/lo operand split; conv2 + tail on FFMA)",
+                entry.update({"bound": "tensor (tcgen05 kind::tf32" + (", single-pass activations" if args.math == "tf32" else
+                                                                        ", exact hi/lo operand split") + "; conv2 + tail on FFMA)",
                               "tensor_share_of_flops": tcf / fl,
-                              "tf32_TFLOPs_issued": 4 * tcf / st["ms_mean"] * 1e-9,
-                              "frac_of_tf32_tensor_peak": 4 * tcf / st["ms_mean"] * 1e-9 / (tensor_peak / 2),
-                              "tf32_peak_note": "dense tf32 taken as half the measured bf16 rate"})
+                              "tf32_TFLOPs_issued": passes * tcf / st["ms_mean"] * 1e-9,
+                              "tf32_issue_utilisation": passes * tcf / st["ms_mean"] * 1e-9 / tf32_peak,
+                              "tf32_peak_TFLOPs": tf32_peak, "tf32_peak_source": tf32_src})
         kernels[name] = entry
     # headline roofline: the fused warp + cost-volume kernel with the largest launch (stage 2)
     dom = max((k for k in kernels if k.startswith(("fused_volume/", "variance_volume/"))), key=lambda k: kernels[k]["algorithmic_bytes"])
@@ -355,7 +502,7 @@ def main():
                 "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"]}
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and wl.key == "config1":
         try:
             with open(traffic_file) as fh:
                 t = json.load(fh)
@@ -371,12 +518,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": MS_WORKLOAD if msred else WORKLOAD,
-                   "class": "Infer_CascadeREDNet" if msred else "Infer_AdaMVSNet", "ndepths": list(nd),
-                   "num_depth": MS_NUM_DEPTH if msred else NUM_DEPTH, "views": V, "batch_per_gpu_per_step": B,
-                   "weights": "seeded random init, calibrated (SURVEY A.6)",
-                   "l2": f"{NSETS} distinct input batches cycled; >1 GB of cost volume written/read per step (>> 126 MB L2)"},
+        "dtype": "f32" if args.math == "fp32" else "tf32", "data": "synthetic",
+        "config": wl.config(B, args.math),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / steps},
         "gpu_launches": launches,
@@ -384,14 +527,32 @@ def main():
         "roofline": roofline,
         "kernels": kernels,
     }
+    if world == 1 and not args.no_library_bar:
+        try:
+            line["library_bar"] = library_bar(wl, model, dev)
+        except Exception as e:                              # the baseline must never take the bench line down
+            line["library_bar"] = {"unavailable": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
-        mps, cores, times = cpu_reference_maps_per_s(n_maps=3, warmup=1, model=args.model)
-        line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "3 depth maps (B=1, same 5-view 768x384 workload), median, after 1 warm-up; "
-                                          "oracle torch-CPU port of the predict class' forward"}
+        n = 3 if wl.key != "config4" else 1
+        mps, cores, times, kind = cpu_reference_maps_per_s(wl, n_maps=n, warmup=1)
+        line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{n} depth maps (B=1, same {V}-view {W}x{H} workload), median, after 1 warm-up; "
+                                          + ("unmodified reference modules (baseline/_ref), Tensor.cuda shimmed to identity"
+                                             if kind == "reference" else "oracle torch-CPU port of the predict class' forward")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _tf32_peak(bf16_peak):
+    """Dense kind::tf32 tcgen05 rate measured by tools/umma_peak_probe.cu on this pool (profiles/tf32_peak.json); until a
+    measurement is committed: half the measured bf16 rate, said so in the line."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "tf32_peak.json")) as f:
+            p = json.load(f)
+        return float(p["tf32_tflops"]), "measured (profiles/tf32_peak.json)"
+    except Exception:
+        return bf16_peak / 2, "assumed: half the measured bf16 rate"
 
 
 if __name__ == "__main__":

@@ -31,14 +31,26 @@ CASES = {
 }
 
 
+def _bind_reference(module):
+    """The reference's models/<module>.py.  Its models/ has no __init__.py and this repo has a package of the same
+    name, so `import models.adamvs` would resolve to OUR drop-in: bind the reference's directory explicitly to a
+    private package name instead (relative imports inside the reference keep working)."""
+    import importlib
+    import types
+    if "refmodels" not in sys.modules:
+        pkg = types.ModuleType("refmodels")
+        pkg.__path__ = [os.path.join(REF, "models")]
+        sys.modules["refmodels"] = pkg
+    mod = importlib.import_module("refmodels." + module)
+    assert mod.__file__.startswith(REF), mod.__file__
+    return mod
+
+
 def main():
     warnings.filterwarnings("ignore")
     sys.path.insert(0, ROOT)
     from adamvs_b200 import synth            # imported before the reference shadows nothing of ours
-    sys.path.insert(0, REF)
-    import importlib
-    ref_adamvs = importlib.import_module("models.adamvs")      # the reference's (namespace package)
-    assert ref_adamvs.__file__.startswith(REF), ref_adamvs.__file__
+    ref_adamvs = _bind_reference("adamvs")
     torch.Tensor.cuda = lambda self, *a, **k: self             # CPU shim for the hard-coded .cuda()
     torch.set_num_threads(os.cpu_count())
 
@@ -113,17 +125,9 @@ def main_msred():
     warnings.filterwarnings("ignore")
     sys.path.insert(0, ROOT)
     from adamvs_b200 import synth
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
     import contextlib
-    import importlib
     import io
-    import types
-    pkg = types.ModuleType("refmodels")                     # the reference's models/ has no __init__.py and our repo has
-    pkg.__path__ = [os.path.join(REF, "models")]            # a package of the same name: bind the directory explicitly
-    sys.modules["refmodels"] = pkg
-    ref = importlib.import_module("refmodels.msrednet")
-    assert ref.__file__.startswith(REF), ref.__file__
+    ref = _bind_reference("msrednet")
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.set_num_threads(os.cpu_count())
     for name, (B, H, W, ndepths, num_depth, gain, wseed, iseed, store) in MSRED_CASES.items():

@@ -477,6 +477,26 @@ def test_msred_forward_full_size_vs_oracle():
     print("msred full-size: reference arithmetic noise (depth rel, prob abs) per stage:", noise)
 
 
+def test_msred_forward_config5_d128_vs_oracle():
+    """BASELINE configs[4] as written: Infer_CascadeREDNet, 5-view 768x384, ndepths 128/32/8, num_depth 512 (the CPU
+    oracle needs a few seconds per forward; it runs twice for the reference's own arithmetic noise)."""
+    from adamvs_b200 import synth
+    from oracle import msrednet_oracle as MO
+    nd = (128, 32, 8)
+    imgs, proj, dv2 = synth.make_sample(1, 384, 768, 5, seed=29)
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 43)
+    f = MO.feature_net(sd, imgs[:, 0])
+    sd = synth.calibrate_msred_state_dict(sd, {k: float(f[k].std()) for k in f}, 4.0)
+    want, noise = _arithmetic_noise(lambda: MO.infer_cascade_rednet_forward(sd, imgs, proj, dv2, num_depth=512, ndepths=nd))
+    m = _msred_model("stream", sd, nd, 512)
+    out = m(imgs.to(_dev()), _to_dev(proj), dv2.to(_dev()))
+    assert tuple(out["stage1"]["depth"].shape) == (1, 96, 192) and tuple(out["depth"].shape) == (1, 384, 768)
+    _compare_msred(out, want, noise, "msred-d128")
+    errs = {s: (rel_err(out[s]["depth"].cpu(), want[s]["depth"]),
+                abs_err(out[s]["photometric_confidence"].cpu(), want[s]["photometric_confidence"])) for s in ("stage1", "stage2", "stage3")}
+    print("msred D=128/32/8: (depth rel, prob abs) ours vs oracle:", errs, "| reference arithmetic noise:", noise)
+
+
 @pytest.mark.parametrize("cfg", ["0", "1", "2"])
 def test_conv_tile_configurations_forced(cfg):
     """The persistent conv kernels pick one of three tile configurations from the plane size (32x16 tiles with 4x2
@@ -722,6 +742,53 @@ def test_config4_oblique_tile_properties(cls_name):
         hi = F.max_pool2d(src.unsqueeze(1), 5, 1, 2).squeeze(1) + hr + 1e-2
         dd = out[s]["depth"]
         assert bool(((dd >= lo) & (dd <= hi)).all()), s
+
+
+@pytest.mark.parametrize("cls", ["stream", "whole"])
+def test_config4_oblique_tile_vs_oracle(cls):
+    """configs[3] against the oracle: 5-view 1536x1536, ndepths 96/32/8 (the pair U-Net has 96 channels: its
+    48-channel tensor-core slices do not apply, it runs on the FFMA kernels), calibrated seeded weights; the
+    north_star's tolerances at every stage.  The CPU oracle needs ~30-45 s per forward at this size."""
+    nd = (96, 32, 8)
+    sd, imgs, proj, dv2, dv3 = make_case(1, 1536, 1536, nd, 192, 60.0, 33, 19, O.feature_net)
+    if cls == "whole":
+        want = O.adamvs_forward(sd, imgs, proj, dv3, ndepths=nd)
+    else:
+        want = O.infer_adamvs_forward(sd, imgs, proj, dv2, num_depth=192, ndepths=nd)
+    m = _model(cls, sd, nd, 192)
+    with torch.no_grad():
+        out = m(imgs.to(_dev()), _to_dev(proj), (dv3 if cls == "whole" else dv2).to(_dev()))
+    assert tuple(out["stage1"]["depth"].shape) == (1, 768, 768) and tuple(out["depth"].shape) == (1, 1536, 1536)
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], want[s]["depth"], want[s]["photometric_confidence"], f"config4/{cls}/{s}")
+    assert float(want["stage1"]["photometric_confidence"].max()) > 5.0 / 96        # not the vacuous 1/D regime
+    assert float(want["stage3"]["photometric_confidence"].max()) > 0.5
+
+
+def test_ops_follow_the_tensors_device_not_the_current_one():
+    """the C library launches on the current device; ops must make the tensors' device current.  With one
+    visible GPU the guard is exercised through a non-default current stream on the same device, and tensors of two
+    devices in one call are refused (when a second GPU exists, the cross-device launch itself is checked)."""
+    ops = _ops()
+    x = torch.randn(2, 3, 8, 12, device=_dev())
+    want = F.interpolate(x, size=(16, 24), mode="bilinear", align_corners=False)
+    side = torch.cuda.Stream(device=_dev())
+    side.wait_stream(torch.cuda.current_stream(_dev()))
+    with torch.cuda.stream(side):
+        got = ops.resize_bilinear(x, 16, 24)
+    side.synchronize()
+    assert abs_err(got.cpu(), want.cpu()) < 1e-6
+    if torch.cuda.device_count() > 1:
+        d1 = torch.device("cuda:1")
+        x1 = x.to(d1)
+        assert torch.cuda.current_device() == 0
+        got1 = ops.resize_bilinear(x1, 16, 24)                # current device is cuda:0, the tensor lives on cuda:1
+        torch.cuda.synchronize(d1)
+        assert got1.device == d1 and abs_err(got1.cpu(), want.cpu()) < 1e-6
+        feat = torch.randn(1, 3, 8, 8, 16, device=_dev())
+        with pytest.raises(ops.AdamvsError):
+            ops.fused_volume(feat, torch.zeros(1, 2, 12, device=d1), ops.Hyp(ops.HYP_PLANES, torch.tensor([[1.0, 2.0]], device=_dev())),
+                             torch.ones(1, 2, 8, 16, device=_dev()), ops.EPS_NUMERATOR, 4)
 
 
 def test_predict_scene_writes_the_reference_output_files(tmp_path):
