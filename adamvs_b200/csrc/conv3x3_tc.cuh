@@ -141,7 +141,7 @@ struct TcCfg {
     static constexpr int NA = 3;                                   // operand stages
     // GRU epilogue operands (h for the reset gates; u and h for the candidate blend) travel like the input: the producer
     // streams [channels][4*MT rows][32] boxes of the output tile into a ring EPI_R tiles deep
-    static constexpr int NGW = (MT * (COUT / 8) + 1) / 2;          // epilogue steps per warp and tile (the last may be empty)
+    static constexpr int NG_STEPS = MT * (COUT / 8);               // (M tile, 8-channel group) epilogue steps per tile
     static constexpr int EPI_CH = EPI == EPI_GATES ? COUT / 2 : (EPI == EPI_CAND ? 2 * COUT : 0);
     static constexpr int EPI_PLANE = G::TH * 32;                   // floats per channel of a box
     static constexpr int EPI_TILE_BYTES = EPI_CH * EPI_PLANE * 4;
@@ -165,12 +165,16 @@ struct TcCfg {
     static_assert(SMEM <= 227 * 1024, "does not fit shared memory");
 };
 
-// warps 0-3 and 12-15: epilogue (TMEM lane quarter = warp % 4; the two sets take alternate steps), 4-7 converters,
-// 8 TMA producer, 9 MMA issuer, 10-11 idle
-constexpr int kTcThreads = 512;
+// warps 0-3 and 12.. : epilogue, NSET sets of four warps (TMEM lane quarter = warp % 4; set s takes steps s, s + NSET, ..),
+// 4-7 converters, 8 TMA producer, 9 MMA issuer, 10-11 idle.  An epilogue step is a latency chain (TMEM load -> shuffles ->
+// MUFU -> stores, ~1 kclk for ~150 instructions).  MEASURED (round 2, bench B = 32, profiles/r2d_k3_epilogue_sets.txt):
+// NSET = 2 / 3 / 4 (512 / 640 / 768 threads, no spills) give K3 stage 1/2/3 = 10.97/21.83/19.61, 10.94/22.08/19.84,
+// 10.97/22.28/20.05 ms - no gain, so the epilogue's warp count is not what bounds these kernels; 2 sets stay.
+constexpr int kTcDefaultSets = 2;
+constexpr int tc_threads(int nset) { return (12 + 4 * (nset - 1)) * 32; }
 
-template <int CA, int CB, int COUT, int EPI, int MT, int PREC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int CA, int CB, int COUT, int EPI, int MT, int PREC, int NSET>
+__global__ void __launch_bounds__(tc_threads(NSET), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH, ConvArgs a, TileGrid tg) {
     using C = TcCfg<CA, CB, COUT, MT, PREC, EPI>;
@@ -201,14 +205,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (tid == 0) {
         for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
-        for (int i = 0; i < 3; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4 * NSET); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 4 * NSET); }
         fence_mbar_init();
     }
     const int wrow = a.wpk_cout > 0 ? a.wpk_cout : COUT, ocout = a.out_cout > 0 ? a.out_cout : COUT;   // slice of a wider layer
     if (tid < COUT) sBias[tid] = (EPI == EPI_RELU || a.bias == nullptr) ? 0.f : __ldg(a.bias + a.co_off + tid);
     // resident weights: [ci][tap][co] -> B operand [ky][chunk][quad][kx: W_hi co | W_lo co][4 ci], split once per CTA
-    for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += kTcThreads) {
+    for (int i = tid; i < 9 * C::NCH * 2 * COUT * 4; i += tc_threads(NSET)) {
         int r = i;
         const int j = r & 3; r >>= 2;
         const int n = r % COUT; r /= COUT;
@@ -350,7 +354,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ===== epilogue (TMEM lane quarter = warp % 4 = image row mt*4 + quarter): runs one tile behind the MMAs.  One warp
         // per scheduler is latency bound (TMEM load -> shuffles -> MUFU -> stores: ~4.4 clk per instruction measured),
         // so two warps per quarter take alternate (M tile, channel group) steps.
-        const int quarter = warp & 3, eset = warp >= 12 ? 1 : 0;
+        const int quarter = warp & 3, eset = warp < 4 ? 0 : ((warp - 12) >> 2) + 1;
+        constexpr int NGW = (C::NG_STEPS + NSET - 1) / NSET;                 // steps per warp and tile (the last may be empty)
         const size_t plane = (size_t)a.hout * a.wout;
         constexpr int CG = 8;                                                // output channels per step
         constexpr int NCG = COUT / CG, NG = MT * NCG;                        // (M tile, channel group) steps per tile
@@ -362,7 +367,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
             const int ox = (rr % tg.tiles_x) * G::TW + lane, oy0 = (rr / tg.tiles_x) * G::TH + quarter;
             auto process = [&](int sI) {
-                const int gi = eset + 2 * sI;
+                const int gi = eset + NSET * sI;
                 const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
                 // GRU operands of this pixel: box row 4*mt + quarter, column (ox0 - aligned box start) + lane
                 const float* opnd = sEpi + (size_t)(ti % (C::EPI_R > 0 ? C::EPI_R : 1)) * (C::EPI_TILE_BYTES / 4)
@@ -425,8 +430,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (C::EPI_R > 0) mbar_wait_bounded(&e_full[ti % (C::EPI_R > 0 ? C::EPI_R : 1)], (ti / (C::EPI_R > 0 ? C::EPI_R : 1)) & 1);
             if (tid == 0) TC_TRACE(2, ti, 1);
 #pragma unroll
-            for (int sI = 0; sI < C::NGW; ++sI)
-                if (eset + 2 * sI < NG) process(sI);                           // steps eset, eset + 2, ... of this warp set
+            for (int sI = 0; sI < NGW; ++sI)
+                if (eset + NSET * sI < NG) process(sI);                        // steps eset, eset + NSET, ... of this warp set
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -462,10 +467,10 @@ struct TcLayer {
         }
         return true;
     }
-    template <int PREC>
-    static cudaError_t launch_prec(ConvPlan& p, int B, cudaStream_t st) {
+    template <int PREC, int NSET>
+    static cudaError_t launch_set(ConvPlan& p, int B, cudaStream_t st) {
         using C = TcCfg<CA, CB, COUT, MT, PREC, EPI>;
-        auto kern = conv3x3_tc_kernel<CA, CB, COUT, EPI, MT, PREC>;
+        auto kern = conv3x3_tc_kernel<CA, CB, COUT, EPI, MT, PREC, NSET>;
         static bool ready[64] = {false};
         int dev = 0;
         cudaGetDevice(&dev);
@@ -480,7 +485,11 @@ struct TcLayer {
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
-        return launch_pdl(kern, dim3(ctas, 1, 1), dim3(kTcThreads), C::SMEM, st, p.tA, p.tB, p.tU, p.tH, p.args, p.tg);
+        return launch_pdl(kern, dim3(ctas, 1, 1), dim3(tc_threads(NSET)), C::SMEM, st, p.tA, p.tB, p.tU, p.tH, p.args, p.tg);
+    }
+    template <int PREC>
+    static cudaError_t launch_prec(ConvPlan& p, int B, cudaStream_t st) {
+        return launch_set<PREC, kTcDefaultSets>(p, B, st);
     }
     static cudaError_t launch(ConvPlan& p, int B, int prec, cudaStream_t st) {
         return prec == PREC_TF32 ? launch_prec<PREC_TF32>(p, B, st) : launch_prec<PREC_FP32X3>(p, B, st);

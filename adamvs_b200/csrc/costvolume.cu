@@ -152,32 +152,42 @@ static int launch_fused_volume(const float* feat, const float* relproj, const Hy
 // ================================================================================================
 // TMA-staged variant (the fast path; needs w % 4 == 0).
 //
-// A block owns a 32x8 pixel tile and KC = 4 adjacent depth planes of one batch item.  Every thread
-// first computes the bilinear cells and weights of its pixel for the 4 planes x VS views; a block-wide
-// min/max gives, per source view, the bounding box of all cells.  When every box fits BW x BH texels
-// (always for the near-fronto-parallel geometry of aerial blocks; otherwise the block takes the
+// A block owns a (32/G) x 8 pixel tile and 4*G adjacent depth planes of one batch item; a thread owns one pixel and
+// kKC = 4 of those planes.  Every thread first computes the bilinear cells and weights of its pixel for its 4 planes x
+// VS views; a block-wide min/max gives, per source view, the bounding box of all cells.  When every box fits
+// BW x BH texels (always for the near-fronto-parallel geometry of aerial blocks; otherwise the block takes the
 // global-gather path below) the source footprint is brought into shared memory by the TMA unit,
 // 4 channels x VS views per stage, double buffered: out-of-image texels arrive as zeros, which is
 // exactly grid_sample's per-corner zero padding, so taps need no clamping or masking.  The gather
 // then is `LDS [cell + immediate]` (no address arithmetic per tap): 16 LDS + 16 FFMA per output.
 // The binding resource is the shared-memory gather rate (16 taps x 4 B per 4-byte output at
-// 128 B/clk/SM), not HBM: DESIGN.md §3.
+// 128 B/clk/SM = one 32-lane wavefront per clock), not HBM: DESIGN.md §3.
+//
+// Lane mapping (round 2).  A warp is (32/G) x-consecutive pixels x G ADJACENT depth planes (lane = plane lane * 32/G +
+// pixel) and the box pitch is 32 words; a thread's planes are k0 + G*kk + its plane lane, so at every tap load the G
+// plane lanes of one pixel work on adjacent planes.  Round 1 used 32 pixels of one plane per warp with pitch 64: 44 % of
+// all shared-memory wavefronts were bank conflicts (profiles/r03c) - 33-word spans when the source magnification exceeds
+// 1 and, in bench, the SCATTER of neighbouring pixels' samples (an untrained stage hands down a white-noise depth map:
+// adjacent pixels sample +-6..12 px apart).  Adjacent planes of ONE pixel, however, sample ~0.15 px apart whatever the
+// depth map looks like: the same texel (a broadcast, free) or its neighbour.  So a warp touches 32/G scattered word groups
+// instead of 32 scattered words.  Measured in bench (profiles/r2b_r2f_k2_stage2_in_bench_b32.txt): G = 2 is the fastest
+// (stage 1/2/3 2.60/4.95/3.67 ms against round 1's 2.90/5.20/3.75; still 43 % conflicts at stage 2, where the handed-down
+// depth is noise); G = 4 (8 pixels x 4 planes) 2.87/5.28/- ms; lanes along the depth axis only (32 planes of one pixel per
+// warp, results transposed through shared memory) removed the conflicts (2.6 %) but cost 53 % more instructions and ran
+// latency-bound: 4.58/7.47/5.44 ms.  G = 2 ships.
+// The same box serves 4*G planes and is 32 texels wide: L2 -> shared-memory traffic per output is half of round 1's.
 // ================================================================================================
-constexpr int kBW = 64, kBH = 12;          // source box per (view, channel).  The row pitch is a multiple of the 32
-                                            // banks, so a warp (32 consecutive x) stays conflict free when a slight
-                                            // rotation makes it straddle two source rows.  What remains are wrap-around
-                                            // conflicts when the source magnification exceeds 1 (32 lanes then span 33
-                                            // words); a 16x2 warp shape with pitch 48 measured no better (profiles/r01f).
+constexpr int kBW = 32, kBH = 12;          // source box per (view, channel): pitch = the 32 banks
 constexpr int kBox = kBW * kBH;
 constexpr int kCK = 4;                      // channels per pipeline stage
 // Rough depth (an untrained or noisy previous stage, oblique geometry) spreads a tile's footprint over more source
 // rows.  The stage buffer is re-cut at run time, per block, into fewer channels of taller boxes: configuration j holds
 // kCK >> j channels of kBH << j rows per view (4x12, 2x24, 1x48) - same bytes, same occupancy, same gather code with
-// another channel stride - and only blocks whose footprint exceeds 64 x 48 texels take the global-gather path.
+// another channel stride - and only blocks whose footprint exceeds 32 x 48 texels take the global-gather path.
 constexpr int kNCfg = 3;
-constexpr int kKC = 4;                      // depth planes per block
-constexpr int kPX = 32, kPY = 8;            // pixel tile
-constexpr int kWvThreads = kPX * kPY;
+constexpr int kKC = 4;                      // depth planes per thread
+constexpr int kPY = 8;                      // pixel rows per block (one warp each); the tile is 32/G pixels wide
+constexpr int kWvThreads = 32 * kPY;
 
 enum { MODE_FUSED = 0, MODE_SCORE = 1, MODE_VARIANCE = 2 };
 
@@ -222,7 +232,7 @@ __device__ __forceinline__ bool cell_taps(const Ray& r, float d, int h, int w, f
 // Global-gather path for one pixel and the block's planes (any geometry).  Same arithmetic as the
 // fast path; used by blocks whose source footprint does not fit the shared-memory box.
 template <int C, int VS, int MODE>
-__device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x, int y, int k0) {
+__device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x, int y, int k0, int kstep) {
     constexpr int V = VS + 1;
     const int hw = a.h * a.w, pix = y * a.w + x;
     const float* ref = a.feat + ((size_t)b * V) * C * hw + pix;
@@ -238,7 +248,7 @@ __device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x
     const float inv = 1.f / (eps_num ? wsum : (1e-5f + wsum));
     const float start = eps_num ? 1e-5f : 0.f;
     for (int kk = 0; kk < kKC; ++kk) {
-        const int k = k0 + kk;
+        const int k = k0 + kk * kstep;
         if (k >= a.D) break;
         const float d = hyp_at(line, k);
         WTaps t[VS];
@@ -276,7 +286,7 @@ __device__ __noinline__ void warp_volume_slow(const WarpVolArgs& a, int b, int x
     }
 }
 
-template <int C, int VS, int MODE>
+template <int C, int VS, int MODE, int G>
 __global__ void __launch_bounds__(kWvThreads, 2)
 warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                        const __grid_constant__ CUtensorMap tm2, WarpVolArgs a, int nk, int force_cfg) {
@@ -288,12 +298,14 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbuf + 2 * STAGE);    // [2]
     int* sbox = reinterpret_cast<int*>(bars + 2);                      // [VS][4] minx, miny, maxx, maxy
 
+    constexpr int PXW = 32 / G;                                        // tile width
     const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    const int px = lane % PXW, pl = lane / PXW;                        // pixel and plane lane (see "Lane mapping")
     const int kchunk = blockIdx.x % nk, tile = blockIdx.x / nk;        // plane chunk fastest: blocks that share a
-    const int tiles_x = (a.w + kPX - 1) / kPX;                         // source footprint run together (L2 hits)
-    const int x = (tile % tiles_x) * kPX + lane, y = (tile / tiles_x) * kPY + row;
+    const int tiles_x = (a.w + PXW - 1) / PXW;                         // source footprint run together (L2 hits)
+    const int x = (tile % tiles_x) * PXW + px, y = (tile / tiles_x) * kPY + row;
     const int b = blockIdx.y;
-    const int k0 = kchunk * kKC;
+    const int k0 = kchunk * (kKC * G) + pl;                            // this thread's planes: k0 + G*kk
     const int hw = a.h * a.w;
     const bool inside = (x < a.w) && (y < a.h);
     const int pix = inside ? y * a.w + x : 0;
@@ -318,7 +330,7 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
 #pragma unroll
             for (int kk = 0; kk < kKC; ++kk) {
                 int x0, y0;
-                const bool ok = cell_taps(ray, hyp_at(line, k0 + kk), a.h, a.w, wv, x0, y0, wt[kk][v]) && inside && (k0 + kk < a.D);
+                const bool ok = cell_taps(ray, hyp_at(line, k0 + G * kk), a.h, a.w, wv, x0, y0, wt[kk][v]) && inside && (k0 + G * kk < a.D);
                 if (ok) { mnx = min(mnx, x0); mxx = max(mxx, x0); mny = min(mny, y0); mxy = max(mxy, y0); }
                 else { x0 = INT_MAX; wt[kk][v][0] = wt[kk][v][1] = wt[kk][v][2] = wt[kk][v][3] = 0.f; }
                 cell[kk][v] = ok ? (((y0 + 1) << 16) | (x0 + 1)) : -1;
@@ -350,7 +362,7 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
     int cfg = rows <= kBH ? 0 : (rows <= 2 * kBH ? 1 : 2);
     if (force_cfg > 0 && force_cfg < kNCfg && cfg < force_cfg) cfg = force_cfg;     // test hook: exercise the tall-box cuts
     if (!fits || rows > (kBH << (kNCfg - 1)) || force_cfg >= kNCfg) {               // block-uniform
-        if (inside) warp_volume_slow<C, VS, MODE>(a, b, x, y, k0);
+        if (inside) warp_volume_slow<C, VS, MODE>(a, b, x, y, k0, G);
         return;
     }
 #pragma unroll
@@ -380,7 +392,7 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
     float* outp = a.out + ((size_t)b * C * a.D + k0) * hw + pix;
     bool kvalid[kKC];
 #pragma unroll
-    for (int kk = 0; kk < kKC; ++kk) kvalid[kk] = inside && (k0 + kk < a.D);
+    for (int kk = 0; kk < kKC; ++kk) kvalid[kk] = inside && (k0 + G * kk < a.D);
 
     auto run = [&](auto cfg_tag) {
         constexpr int CFG = decltype(cfg_tag)::value;
@@ -437,7 +449,7 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
                             const float m = sum / (float)V;
                             r = sq / (float)V - m * m;
                         }
-                        st_cs_pred(outp + (size_t)cc * plane_stride + (size_t)kk * hw, r, kvalid[kk]);
+                        st_cs_pred(outp + (size_t)cc * plane_stride + (size_t)(G * kk) * hw, r, kvalid[kk]);
                     }
                 }
             }
@@ -459,7 +471,7 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
 #pragma unroll
             for (int v = 0; v < VS; ++v)
                 if (kvalid[kk])
-                    a.out[(((size_t)b * VS + v) * a.D + k0 + kk) * hw + pix] =
+                    a.out[(((size_t)b * VS + v) * a.D + k0 + G * kk) * hw + pix] =
                         acc[MODE == MODE_SCORE ? kk : 0][MODE == MODE_SCORE ? v : 0] / (float)C;
     }
 }
@@ -468,41 +480,46 @@ warp_volume_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
 template <int C, int VS, int MODE>
 __global__ void __launch_bounds__(kWvThreads)
 warp_volume_plain_kernel(WarpVolArgs a, int nk) {
-    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;            // 32 x 8 pixels, kKC contiguous planes
     const int kchunk = blockIdx.x % nk, tile = blockIdx.x / nk;
-    const int tiles_x = (a.w + kPX - 1) / kPX;
-    const int x = (tile % tiles_x) * kPX + lane, y = (tile / tiles_x) * kPY + row;
-    if (x < a.w && y < a.h) warp_volume_slow<C, VS, MODE>(a, blockIdx.y, x, y, kchunk * kKC);
+    const int tiles_x = (a.w + 31) / 32;
+    const int x = (tile % tiles_x) * 32 + lane, y = (tile / tiles_x) * 8 + row;
+    if (x < a.w && y < a.h) warp_volume_slow<C, VS, MODE>(a, blockIdx.y, x, y, kchunk * kKC, 1);
 }
 
 template <int C, int VS, int MODE>
 static int launch_warp_volume_plain(const WarpVolArgs& a, int B, cudaStream_t st) {
     const int nk = (a.D + kKC - 1) / kKC;
-    const long long tiles = (long long)((a.w + kPX - 1) / kPX) * ((a.h + kPY - 1) / kPY);
+    const long long tiles = (long long)((a.w + 31) / 32) * ((a.h + 7) / 8);
     if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
     dim3 grid((unsigned)(tiles * nk), B, 1);
-    warp_volume_plain_kernel<C, VS, MODE><<<grid, kWvThreads, 0, st>>>(a, nk);
+    warp_volume_plain_kernel<C, VS, MODE><<<grid, 256, 0, st>>>(a, nk);
+    ADAMVS_LAUNCH_RESULT();
+}
+
+template <int C, int VS, int MODE, int G>
+static int launch_warp_volume_tma_g(const WarpVolArgs& a, int B, const CUtensorMap* tm, int force_cfg, cudaStream_t st) {
+    constexpr size_t smem = sizeof(float) * 2 * VS * kCK * kBox + 2 * sizeof(uint64_t) + VS * 4 * sizeof(int);
+    auto kern = warp_volume_tma_kernel<C, VS, MODE, G>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int nk = (a.D + kKC * G - 1) / (kKC * G);
+    const long long tiles = (long long)((a.w + 32 / G - 1) / (32 / G)) * ((a.h + kPY - 1) / kPY);
+    if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
+    dim3 grid((unsigned)(tiles * nk), B, 1);
+    kern<<<grid, kWvThreads, smem, st>>>(tm[0], tm[1], tm[2], a, nk, force_cfg);
     ADAMVS_LAUNCH_RESULT();
 }
 
 template <int C, int VS, int MODE>
 static int launch_warp_volume_tma(const WarpVolArgs& a, int B, cudaStream_t st) {
-    constexpr size_t smem = sizeof(float) * 2 * VS * kCK * kBox + 2 * sizeof(uint64_t) + VS * 4 * sizeof(int);
     CUtensorMap tm[kNCfg];
     for (int j = 0; j < kNCfg; ++j)
         if (!make_tmap_4d(&tm[j], a.feat, a.w, a.h, 1, (long long)B * (VS + 1) * C, kBW, kBH << j, kCK >> j)) return -100;
     // test hook (read once per process, like ADAMVS_CONV_CFG): ADAMVS_WARP_CFG=1|2 forces the taller box cuts, 3 the
     // global-gather path, so that parity tests cover every path on smooth synthetic depth
     static const int force_cfg = [] { const char* e = getenv("ADAMVS_WARP_CFG"); return (e && *e >= '0' && *e <= '3') ? (*e - '0') : 0; }();
-    auto kern = warp_volume_tma_kernel<C, VS, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int nk = (a.D + kKC - 1) / kKC;
-    const long long tiles = (long long)((a.w + kPX - 1) / kPX) * ((a.h + kPY - 1) / kPY);
-    if (tiles * nk > 0x7fffffffLL) return ADAMVS_EINVAL;
-    dim3 grid((unsigned)(tiles * nk), B, 1);
-    kern<<<grid, kWvThreads, smem, st>>>(tm[0], tm[1], tm[2], a, nk, force_cfg);
-    ADAMVS_LAUNCH_RESULT();
+    return launch_warp_volume_tma_g<C, VS, MODE, 2>(a, B, tm, force_cfg, st);
 }
 
 // TMA needs 16-byte aligned rows: w % 4 == 0 and a 16-byte aligned base; C a multiple of the stage depth.

@@ -348,6 +348,26 @@ extern "C" int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_we
                                     workspace, workspace_floats, depth, conf, logits_out, B, C, D, h, w, stream);
 }
 
+// L2-resident sub-batching.  One plane step touches, per batch item, four 8-channel full-resolution tensors, four
+// 16-channel half-resolution ones, one plane of the volume and one of the logits; with the whole batch in one launch
+// (B = 32: 300 MB per 8-channel tensor at stage 3) every kernel of the chain reads its predecessor's output back
+// from HBM.  The sweep is therefore run over sub-batches whose working set fits the 126 MB L2, re-using the SAME
+// workspace slots for every sub-batch, so x1 / r*h / u / the GRU states stay in L2 from the kernel that writes them
+// to the kernels that read them.
+// MEASURED (B200, bench B = 32, profiles/r2c_k3_l2_subbatch_sweep.txt): it is a LOSS - stage 1/2/3 10.9/21.9/19.6 ms with
+// whole-batch launches against 14.4/33.8/28.8 ms at a 72 MB budget (48 MB: 16.9/41.8/28.8; 110 MB: 12.6/29.1/28.8): the
+// launches shrink to ~10 us, where per-launch prologue (weight split, TMEM allocation) and tile-quantisation tails cost
+// more than the L2 hits return.  Default therefore OFF (0 = one launch over the whole batch); ADAMVS_K3_L2_MB=<MB>
+// enables it for measurements.
+static int l2_budget_mb() {
+    static const int mb = [] { const char* e = getenv("ADAMVS_K3_L2_MB"); return e ? atoi(e) : 0; }();
+    return mb;
+}
+
+static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, const Workspace& ws, const HypSpec& hs,
+                        const float2* hlines, int out_up, int prob_mode, int math_mode, float* logits,
+                        float* depth, float* conf, int B, int C, int D, int h, int w, cudaStream_t st);
+
 extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet_weights* hwts,
                                         int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
                                         int out_up, int prob_mode, int math_mode,
@@ -366,10 +386,9 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
     Workspace ws = carve(workspace, B, C, D, h, w, out_up);
     if (ws.total > workspace_floats) return ADAMVS_ENOSPACE;
     const HypSpec hs{hyp_mode, hyp_src, hyp_ncol, half_range};
-    const int h2 = h / 2, w2 = w / 2;
-    const size_t hw = (size_t)h * w, hw2 = (size_t)h2 * w2;
+    const size_t hw = (size_t)h * w, hw2 = (size_t)(h / 2) * (w / 2), ohw = out_up ? 4 * hw : hw;
 
-    // one-off per call: weights into [ci][tap][co]; states to zero (adamvs.py:175-176 / 448-449)
+    // one-off per call: weights into [ci][tap][co]
     auto pack = [&](const float* src, float* dst, int cout, int cin, int tr) {
         const int n = cout * cin * 9;
         pack_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, cout, cin, tr, 0);
@@ -382,16 +401,45 @@ extern "C" int adamvs_regnet_red_ex_f32(const float* volume, const adamvs_regnet
     pack(hwts->cand2_w, ws.pk_cand2, 16, 32, 0);
     pack(hwts->up1_w, ws.pk_up1, 8, 16, 1);
     ADAMVS_TRY(cudaGetLastError());
-    ADAMVS_TRY(cudaMemsetAsync(ws.h1, 0, sizeof(float) * B * 8 * hw, st));
-    ADAMVS_TRY(cudaMemsetAsync(ws.h2, 0, sizeof(float) * B * 16 * hw2, st));
-    const OutWeights ow{hwts->out_w, hwts->out_b};
     float* logits = logits_out ? logits_out : ws.logits;
-    const float2* hlines = nullptr;                       // per-pixel hypothesis lines for the tail (in ws.y: y itself
+    const float2* hlines = nullptr;                       // per-pixel hypothesis lines for the regression (in ws.y: y itself
     if (hyp_mode == ADAMVS_HYP_PER_PIXEL) {               // never leaves shared memory since the tail was fused)
         hyp_lines_kernel<<<(unsigned)(((size_t)B * hw + 255) / 256), 256, 0, st>>>(hs, reinterpret_cast<float2*>(ws.y), B, (int)hw, D);
         ADAMVS_TRY(cudaGetLastError());
         hlines = reinterpret_cast<const float2*>(ws.y);
     }
+
+    // sub-batches sized to the L2 budget, balanced
+    const double item_bytes = 4.0 * (4.0 * 8 * hw + 4.0 * 16 * hw2 + (double)C * hw + (double)ohw);
+    int Bs = B;
+    if (l2_budget_mb() > 0) {
+        long long fit = (long long)(l2_budget_mb() * 1048576.0 / item_bytes);
+        if (fit < 1) fit = 1;
+        if (fit < B) { const int nsub = (int)((B + fit - 1) / fit); Bs = (B + nsub - 1) / nsub; }
+    }
+    for (int b0 = 0; b0 < B; b0 += Bs) {
+        const int nb = (B - b0 < Bs) ? B - b0 : Bs;
+        HypSpec hsub = hs;
+        hsub.src = hyp_src + (hyp_mode == ADAMVS_HYP_PLANES ? (size_t)b0 * hyp_ncol : (size_t)b0 * hw);
+        const int rc = regnet_sweep(volume + (size_t)b0 * C * D * hw, hwts, ws, hsub, hlines ? hlines + (size_t)b0 * hw : nullptr,
+                                    out_up, prob_mode, math_mode, logits + (size_t)b0 * D * ohw, depth + (size_t)b0 * ohw,
+                                    conf + (size_t)b0 * ohw, nb, C, D, h, w, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+// One sweep over the D planes for B (sub-batch) items in workspace slots 0 .. B-1, then their regression.
+static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, const Workspace& ws, const HypSpec& hs,
+                        const float2* hlines, int out_up, int prob_mode, int math_mode, float* logits,
+                        float* depth, float* conf, int B, int C, int D, int h, int w, cudaStream_t st) {
+    const int h2 = h / 2, w2 = w / 2;
+    const size_t hw = (size_t)h * w, hw2 = (size_t)h2 * w2;
+    // states to zero (adamvs.py:175-176 / 448-449)
+    ADAMVS_TRY(cudaMemsetAsync(ws.h1, 0, sizeof(float) * B * 8 * hw, st));
+    ADAMVS_TRY(cudaMemsetAsync(ws.h2, 0, sizeof(float) * B * 16 * hw2, st));
+    const OutWeights ow{hwts->out_w, hwts->out_b};
+    float* workspace = ws.pk_conv1;                         // alignment check below: the carve starts here
 
     // ---- per-layer arguments (fixed for the whole sweep; only conv1's plane index changes)
     ConvArgs a1{}, a2{}, a3{}, a4{}, a5{}, a6{};

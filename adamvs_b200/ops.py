@@ -29,6 +29,8 @@ EXPORTS = (
     "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
     "adamvs_deconv3x3_supported", "adamvs_deconv3x3_f32",
     "adamvs_context_head_supported", "adamvs_context_head_f32",
+    "adamvs_conv2d_f32", "adamvs_conv2d_wgrad_f32", "adamvs_pair_score_bwd_f32", "adamvs_fused_volume_bwd_f32",
+    "adamvs_softmax_expect_f32", "adamvs_softmax_expect_bwd_f32",
 )
 
 
@@ -82,6 +84,12 @@ def lib() -> ctypes.CDLL:
         L.adamvs_context_head_supported.argtypes = [ci, ci, ci]
         L.adamvs_context_head_f32.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv3x3_f32.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, vp]
+        L.adamvs_conv2d_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_conv2d_wgrad_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_pair_score_bwd_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_fused_volume_bwd_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.adamvs_softmax_expect_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+        L.adamvs_softmax_expect_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
         for name in EXPORTS:
             if name not in ("adamvs_abi_version", "adamvs_regnet_red_workspace_floats",
                             "adamvs_regnet_msred_workspace_floats"):

@@ -206,6 +206,45 @@ int adamvs_deconv3x3_supported(int CIN, int COUT);
 int adamvs_deconv3x3_f32(const float* in, const float* wpk, const float* bias, int relu, float* out,
                          int N, int CIN, int COUT, int hin, int win, void* stream);
 
+/* ---- Training path: backward kernels, csrc/train.cu ------------------------------------------- */
+
+/* 3x3 convolution with run-time channel counts, the building block of the regulariser's training forward and of every
+ * data gradient (reference layers: models/adamvs.py:157-195, models/module.py:24-52):
+ *   transposed = 0: y = act(conv2d(x, w [Cout,Cin,3,3], bias, stride 1|2, padding 1))
+ *   transposed = 1: y = act(conv_transpose2d(x, w [Cin,Cout,3,3], bias, stride 2, padding 1, output_padding 1))
+ * Data gradients: of a stride-1 conv = this op on the output gradient with the flipped, transposed weight; of a stride-2
+ * conv = the transposed form with the SAME weight tensor; of the transposed conv = the stride-2 conv form with the same
+ * weight tensor.  bias may be NULL.  x: [N,Cin,hin,win]; y: [N,Cout,hout,wout]. */
+int adamvs_conv2d_f32(const float* x, const float* w, const float* bias, float* y, int N, int Cin, int Cout,
+                      int hin, int win, int stride, int transposed, int relu, void* stream);
+
+/* Weight gradient of conv2d(x, w [Cout,Cin,3,3], stride 1|2, padding 1): gw += sum_{n,pixels} gy * x (gw zeroed by the
+ * caller; atomics).  The transposed conv's weight gradient is the same call with x = its output gradient and gy = its
+ * input (stride 2), which yields its [Cin,Cout,3,3] layout.  x: [N,Cin,hin,win]; gy: [N,Cout,hin/stride,win/stride]. */
+int adamvs_conv2d_wgrad_f32(const float* x, const float* gy, float* gw, int N, int Cin, int Cout,
+                            int hin, int win, int stride, void* stream);
+
+/* Backward of adamvs_pair_score_f32 (K1): g_feat [B,V,C,h,w] += d score / d feat (zeroed by the caller).  The sampling
+ * grid carries no gradient (models/module.py:538). */
+int adamvs_pair_score_bwd_f32(const float* feat, const float* relproj,
+                              int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                              const float* g_score, float* g_feat, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* Backward of adamvs_fused_volume_f32 (K2): g_feat [B,V,C,h,w] and g_weights [B,V-1,h,w], both += (zeroed by the caller). */
+int adamvs_fused_volume_bwd_f32(const float* feat, const float* relproj,
+                                int hyp_mode, const float* hyp_src, int hyp_ncol, const float* half_range,
+                                const float* weights, int eps_mode, const float* g_volume,
+                                float* g_feat, float* g_weights, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* K4 in its training form: softmax over D, expectation over a materialised hypothesis tensor, max probability
+ * (adamvs.py:306-310, module.py:617-625), and its backward (g_depth / g_conf may be NULL = zero; g_hyp may be NULL).
+ * logits, hyp, g_logits, g_hyp: [N,D,h,w]; depth, conf, g_depth, g_conf: [N,h,w]. */
+int adamvs_softmax_expect_f32(const float* logits, const float* hyp, float* depth, float* conf,
+                              int N, int D, int h, int w, void* stream);
+int adamvs_softmax_expect_bwd_f32(const float* logits, const float* hyp, const float* depth,
+                                  const float* g_depth, const float* g_conf, float* g_logits, float* g_hyp,
+                                  int N, int D, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
