@@ -44,8 +44,9 @@ def forward(net, imgs: torch.Tensor, proj_matrices: Dict[str, torch.Tensor], dep
     if not imgs.is_cuda:
         raise ops.AdamvsError("adamvs_b200 runs on CUDA tensors only (no CPU fallback)")
     if torch.is_grad_enabled() and net.training:
-        raise NotImplementedError("adamvs_b200 has forward kernels only so far: call under torch.no_grad() "
-                                  "or model.eval() (train_whu.py --mode test/profile, predict_whu.py)")
+        # train_whu.py --mode train: the differentiable forward over the forward / backward kernels (autograd.py)
+        from . import autograd
+        return autograd.forward_train(net, imgs, proj_matrices, depth_values)
     with torch.no_grad():
         return _forward(net, imgs, proj_matrices, depth_values, capture)
 

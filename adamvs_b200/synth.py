@@ -34,17 +34,16 @@ def _rot_y(a: float) -> np.ndarray:
     return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=np.float64)
 
 
-def make_cameras(height: int, width: int, num_src: int = 4, jitter_seed: int | None = None) -> Dict[str, torch.Tensor]:
-    """Look-at rig: reference camera at the origin looking down +z, source cameras on baselines of
-    up to 60 m, all aimed at (0, 0, 600). Returns {"stageN": [V,4,4] float32}.
+def camera_rig(height: int, width: int, num_src: int = 4, jitter_seed: int | None = None):
+    """Look-at rig: reference camera at the origin looking down +z, source cameras on baselines of up to 60 m, all aimed
+    at (0, 0, 600).  Returns (K [3,3], [(R [3,3], t [3]) per view]) in float64, world -> camera (X right, Y down).
 
     With jitter_seed the baselines are perturbed by a few metres so that a batch of reference views
-    does not share one geometry.
-    """
+    does not share one geometry."""
     f = 1.2 * width
     K = np.array([[f, 0, width / 2.0], [0, f, height / 2.0], [0, 0, 1]], dtype=np.float64)
     rng = np.random.default_rng(1000003 + jitter_seed) if jitter_seed is not None else None
-    mats = []
+    poses = []
     for v in range(num_src + 1):
         if v == 0:
             R = np.eye(3)
@@ -58,7 +57,16 @@ def make_cameras(height: int, width: int, num_src: int = 4, jitter_seed: int | N
             yaw = math.atan2(-bx, LOOK_AT_Z)
             pitch = math.atan2(by, LOOK_AT_Z)
             R = (_rot_y(yaw) @ _rot_x(pitch)).T
-        t = -R @ c
+        poses.append((R, -R @ c))
+    return K, poses
+
+
+def make_cameras(height: int, width: int, num_src: int = 4, jitter_seed: int | None = None) -> Dict[str, torch.Tensor]:
+    """Projection matrices of camera_rig(): {"stageN": [V,4,4] float32} with K[R|t] in the top three rows and rows 0-1
+    divided by 4 / 2 / 1."""
+    K, poses = camera_rig(height, width, num_src, jitter_seed)
+    mats = []
+    for R, t in poses:
         P = np.eye(4)
         P[:3, :3] = K @ R
         P[:3, 3] = K @ t

@@ -64,3 +64,42 @@ def abs_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).abs().max())
+
+
+def make_blendedmvs_scene(root, height=64, width=96, views=5, num_depth=32, seed=4):
+    """A tiny training scene in the BlendedMVS layout the reference's datasets/cas_total_rscv.py reads
+    (BlendedMVS_list :164-207, tr_read_blendedmvs_cam :357-386): index.txt, <scene>/blended_images/%08d.jpg,
+    <scene>/cams/%08d_cam.txt (Tcw, K, depth start / interval / count / end), <scene>/cams/pair.txt,
+    <scene>/rendered_depth_maps/%08d.pfm.  Synthetic rig and texture of adamvs_b200.synth; two reference views."""
+    from PIL import Image
+    from adamvs_b200 import sceneio as S
+    scene = os.path.join(root, "scene0")
+    for d in ("blended_images", "cams", "rendered_depth_maps"):
+        os.makedirs(os.path.join(scene, d), exist_ok=True)
+    with open(os.path.join(root, "index.txt"), "w") as f:
+        f.write("scene0\n")
+    K, poses = synth.camera_rig(height, width, views - 1)
+    imgs = synth.make_images(views, height, width, seed)                       # [V,3,H,W], zero mean / unit variance
+    interval = (synth.DEPTH_MAX - synth.DEPTH_MIN) / num_depth
+    for v in range(views):
+        a = imgs[v].permute(1, 2, 0).numpy()
+        a = np.clip(a * 48.0 + 128.0, 0, 255).astype(np.uint8)
+        Image.fromarray(a).save(os.path.join(scene, "blended_images", f"{v:08d}.jpg"), quality=95)
+        R, t = poses[v]
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, t
+        with open(os.path.join(scene, "cams", f"{v:08d}_cam.txt"), "w") as f:
+            f.write("extrinsic\n" + "\n".join(" ".join(f"{x:.10f}" for x in row) for row in T) + "\n\n")
+            f.write("intrinsic\n" + "\n".join(" ".join(f"{x:.10f}" for x in row) for row in K) + "\n\n")
+            f.write(f"{synth.DEPTH_MIN} {interval} {num_depth} {synth.DEPTH_MAX}\n")
+    with open(os.path.join(scene, "cams", "pair.txt"), "w") as f:
+        f.write("2\n")
+        for ref in (0, 1):
+            others = [v for v in range(views) if v != ref]
+            f.write(f"{ref}\n{len(others)} " + " ".join(f"{v} 1.0" for v in others) + "\n")
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    for ref in (0, 1):
+        depth = (600.0 + 25.0 * np.sin(xx / 17.0 + ref) * np.cos(yy / 13.0) + rng.uniform(-1, 1)).astype(np.float32)
+        S.write_pfm(os.path.join(scene, "rendered_depth_maps", f"{ref:08d}.pfm"), depth)
+    return root

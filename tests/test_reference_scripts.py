@@ -110,3 +110,42 @@ def test_reference_predict_script_runs_unchanged_on_the_dropin(tmp_path):
         assert rel_err(torch.from_numpy(mine[k][0]), torch.from_numpy(ours[k][0])) < 1e-5, k
         assert abs_err(torch.from_numpy(mine[k][1]), torch.from_numpy(ours[k][1])) < 1e-5, k
         assert mine[k][2] == ours[k][2], k
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_train_script_runs_unchanged_on_the_dropin(tmp_path):
+    """train_whu.py --mode train (unmodified, from baseline/_ref) with this repo's models/ first on sys.path: one epoch
+    over a two-sample BlendedMVS-layout scene.  Its own loop does model.train() -> forward -> cas_mvs_vis_loss ->
+    backward -> RMSprop step (train_whu.py:265-300), saves checkpoints, then evaluates with model.eval() under no_grad
+    (the inference kernels) and writes train_record.txt.  Checked: finite losses, a checkpoint whose weights moved
+    and stayed finite, the evaluation record."""
+    import re
+    from tests.helpers import make_blendedmvs_scene
+    from tools.run_reference_script import make_checkpoint
+    root = make_blendedmvs_scene(str(tmp_path / "train"))
+    sd = _state_dict()
+    ck = str(tmp_path / "init.ckpt")
+    make_checkpoint(ck, sd)
+    logdir = str(tmp_path / "log")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), "--script", "train_whu.py", "--models", "ours", "--",
+           "--mode", "train", "--model", "adamvs", "--set_name", "BlendedMVS", "--dataset", "cas_total_rscv",
+           "--trainpath", root, "--testpath", root, "--loadckpt", ck, "--logdir", logdir, "--view_num", "5",
+           "--ndepths", ",".join(map(str, NDEPTHS)), "--epochs", "1", "--summary_freq", "1", "--batch_size", "1", "--lr", "0.0005"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    losses = [float(x) for x in re.findall(r"train loss = ([0-9.eE+-]+|nan|inf)", r.stdout)]
+    assert len(losses) == 2 and all(np.isfinite(l) and l > 0 for l in losses), r.stdout[-2000:]
+    tests_ = re.findall(r"test loss = ([0-9.eE+-]+|nan|inf)", r.stdout)
+    assert len(tests_) == 2 and all(np.isfinite(float(x)) for x in tests_), r.stdout[-2000:]
+    assert os.path.isfile(os.path.join(logdir, "train_record.txt"))
+    saved = torch.load(os.path.join(logdir, "model_000000.ckpt"), map_location="cpu")
+    moved, n = 0, 0
+    for k, v in saved["model"].items():
+        assert torch.isfinite(v.float()).all(), k
+        k0 = k[len("module."):]
+        if v.dtype.is_floating_point and k0 in sd and "running" not in k0:
+            n += 1
+            moved += int(not torch.equal(v, sd[k0]))
+    # every parameter the forward uses received a gradient and an RMSprop step; DepthNet.1/2.reg are never executed
+    assert moved >= 120 and moved < n, (moved, n)
