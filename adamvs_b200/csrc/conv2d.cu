@@ -10,7 +10,7 @@
 namespace adamvs {
 
 template <int CA, int CB, int COUT, int STRIDE>
-static int run_conv(const ConvArgs& a, int N, cudaStream_t st) {
+static int run_conv(const ConvArgs& a, int N, cudaStream_t st, bool tma_only = false) {
     constexpr int COB = COUT % 16 == 0 ? 16 : 8;
     using L = ConvLayer<CA, CB, COUT, COB, STRIDE, EPI_BIAS>;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.inA) | reinterpret_cast<uintptr_t>(a.inB) |
@@ -55,6 +55,7 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st) {
             return e == cudaSuccess ? 0 : (int)e;
         }
     }
+    if (tma_only) return ADAMVS_EINVAL;                // the pointer-arithmetic kernel would read past a narrower tensor
     using G = TileGeom<STRIDE, 16, 16>;
     constexpr size_t smem = sizeof(float) * ((CA + CB) * 9 * COB + CK * G::IH * G::IP);
     auto kern = conv3x3_kernel<CA, CB, COUT, COB, STRIDE, EPI_BIAS, 16, 16>;
@@ -148,6 +149,7 @@ static int launch_context_head(const float* x, const float* a, const float* c, c
 using namespace adamvs;
 
 extern "C" int adamvs_conv3x3_supported(int CA, int CB, int COUT, int stride) {
+    if (stride == 1 && CA == 3 && CB == 0 && COUT == 8) return 1;     // the 3-channel image: one 8-channel chunk, see adamvs_conv3x3_f32
     if (stride == 1) {
         if (CB == 0) return (CA == 8 && COUT == 8) || (CA == 16 && COUT == 16) || (CA == 32 && COUT == 32) || (CA == 48 && COUT == 48) ||
                             (CA == 32 && COUT == 16) || (CA == 64 && COUT == 32);     // the 5x5 stride-2 convs in polyphase form
@@ -169,6 +171,14 @@ extern "C" int adamvs_conv3x3_f32(const float* inA, int CA, const float* inB, in
     a.wpk = wpk; a.bias = bias; a.out0 = out; a.relu = relu;
     a.hin = hin; a.win = win; a.hout = hout; a.wout = wout;
     cudaStream_t st = (cudaStream_t)stream;
+    if (CA == 3) {
+        // FeatureNet0's first layer reads the 3-channel image in place (no zero-padded copy): the TMA box of the one
+        // 8-channel chunk starts at plane 3n; its planes 3..7 are the next image's (finite) channels - or the tensor map's
+        // zero fill behind the last image - and meet zero weights (wpk rows 3..7 are zero by contract).
+        ADAMVS_CHECK_ARG(win % 4 == 0 && reinterpret_cast<uintptr_t>(inA) % 16 == 0);
+        a.strideA_b = 3LL * (long long)hw; a.planesA = 3;
+        return run_conv<8, 0, 8, 1>(a, N, st, true);
+    }
     if (stride == 2) return run_conv<48, 0, 48, 2>(a, N, st);
     if (CB == 16) return run_conv<16, 16, 16, 1>(a, N, st);
     if (CB == 8) return run_conv<8, 8, 8, 1>(a, N, st);
@@ -188,7 +198,7 @@ namespace adamvs {
 template <int CIN, int COUT>
 static __global__ void __launch_bounds__(128)
 deconv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ bias, int relu,
-                 float* __restrict__ out, int hin, int win) {
+                 const float* __restrict__ residual, float* __restrict__ out, int hin, int win) {
     constexpr int COB = 8;
     __shared__ float sW[CIN * 9 * COB];
     const int cob = blockIdx.y % (COUT / COB), iy = blockIdx.y / (COUT / COB);
@@ -228,16 +238,20 @@ deconv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wpk, co
         float r[4] = {acc[0][c] + bc, acc[1][c] + bc, acc[2][c] + bc, acc[3][c] + bc};
         if (relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
         const size_t o = ((size_t)b * COUT + cob * COB + c) * 4 * ip + (size_t)(2 * iy) * wout + 2 * ix;
+        if (residual) {                                  // skip connection added after the activation (adamvs.py:233-235)
+            const float2 s0 = *reinterpret_cast<const float2*>(residual + o), s1 = *reinterpret_cast<const float2*>(residual + o + wout);
+            r[0] += s0.x; r[1] += s0.y; r[2] += s1.x; r[3] += s1.y;
+        }
         *reinterpret_cast<float2*>(out + o) = make_float2(r[0], r[1]);
         *reinterpret_cast<float2*>(out + o + wout) = make_float2(r[2], r[3]);
     }
 }
 
 template <int CIN, int COUT>
-static int launch_deconv(const float* in, const float* wpk, const float* bias, int relu, float* out, int N, int hin, int win, cudaStream_t st) {
+static int launch_deconv(const float* in, const float* wpk, const float* bias, int relu, const float* residual, float* out, int N, int hin, int win, cudaStream_t st) {
     if ((long long)hin * (COUT / 8) > 65535 || N > 65535) return ADAMVS_EINVAL;
     dim3 grid((win + 127) / 128, hin * (COUT / 8), N);
-    deconv3x3_kernel<CIN, COUT><<<grid, 128, 0, st>>>(in, wpk, bias, relu, out, hin, win);
+    deconv3x3_kernel<CIN, COUT><<<grid, 128, 0, st>>>(in, wpk, bias, relu, residual, out, hin, win);
     ADAMVS_LAUNCH_RESULT();
 }
 }  // namespace adamvs
@@ -246,14 +260,106 @@ extern "C" int adamvs_deconv3x3_supported(int CIN, int COUT) {
     return (CIN == 32 && COUT == 16) || (CIN == 16 && COUT == 8) || (CIN == 48 && COUT == 48);
 }
 
+extern "C" int adamvs_deconv3x3_res_f32(const float* in, const float* wpk, const float* bias, int relu, const float* residual,
+                                        float* out, int N, int CIN, int COUT, int hin, int win, void* stream) {
+    ADAMVS_CHECK_ARG(in && wpk && bias && out && N > 0 && hin > 0 && win > 0 && adamvs_deconv3x3_supported(CIN, COUT));
+    ADAMVS_CHECK_ARG((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) % 8 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (CIN == 32) return launch_deconv<32, 16>(in, wpk, bias, relu, residual, out, N, hin, win, st);
+    if (CIN == 16) return launch_deconv<16, 8>(in, wpk, bias, relu, residual, out, N, hin, win, st);
+    return launch_deconv<48, 48>(in, wpk, bias, relu, residual, out, N, hin, win, st);
+}
+
 extern "C" int adamvs_deconv3x3_f32(const float* in, const float* wpk, const float* bias, int relu, float* out,
                                     int N, int CIN, int COUT, int hin, int win, void* stream) {
-    ADAMVS_CHECK_ARG(in && wpk && bias && out && N > 0 && hin > 0 && win > 0 && adamvs_deconv3x3_supported(CIN, COUT));
-    ADAMVS_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 8 == 0);
+    return adamvs_deconv3x3_res_f32(in, wpk, bias, relu, nullptr, out, N, CIN, COUT, hin, win, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// adamvs_context_pool_f32 - the two pooled-context branches in front of a FeatureNet0 output head (reference
+// models/adamvs.py:112-147: AvgPool2d(4) / AvgPool2d(8) -> 1x1 conv -> BatchNorm -> ReLU), eval-mode BatchNorm folded:
+//     a = relu(Wa * avgpool4(x) + ba)   [N,CO,h/4,w/4]        c = relu(Wc * avgpool8(x) + bc)   [N,CO,h/8,w/8]
+// One pass over x.  A thread owns one 4x4 block (four float4 row loads per channel, coalesced across the warp) and keeps
+// the C pooled values in registers; the four threads of an 8x8 cell sit in lanes l, l^1 (x), l^2 (y) and combine by
+// shuffle (the mean of four equal-sized means).  The 1x1 convolutions run from shared-memory weights.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C, int CO>
+__global__ void __launch_bounds__(128)
+context_pool_kernel(const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ ba,
+                    const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ a, float* __restrict__ c,
+                    int h, int w) {
+    __shared__ float sWa[C * CO], sWc[C * CO], sBa[CO], sBc[CO];
+    for (int i = threadIdx.x; i < C * CO; i += 128) { sWa[i] = __ldg(wa + i); sWc[i] = __ldg(wc + i); }     // [co][ci]
+    if (threadIdx.x < CO) { sBa[threadIdx.x] = __ldg(ba + threadIdx.x); sBc[threadIdx.x] = __ldg(bc + threadIdx.x); }
+    __syncthreads();
+    const int h4 = h / 4, w4 = w / 4, h8 = h / 8, w8 = w / 8;
+    // lane -> (x bit, y bit, cell): lanes l, l^1, l^2, l^3 are the 2x2 blocks of one 8x8 cell
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int cell = (blockIdx.x * 4 + wrp) * 8 + (lane >> 2);         // 8x8 cell along x
+    const int cy = blockIdx.y, n = blockIdx.z;
+    const int bx = 2 * cell + (lane & 1), by = 2 * cy + ((lane >> 1) & 1);   // 4x4 block coordinates
+    const bool in = cell < w8;
+    float p4[C];
+    const float* px = x + (size_t)n * C * h * w + (size_t)(4 * by) * w + 4 * bx;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        float s = 0.f;
+        if (in) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(px + (size_t)ch * h * w + (size_t)r * w));
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+        }
+        p4[ch] = s * (1.f / 16.f);
+    }
+    if (in) {
+#pragma unroll 2
+        for (int co = 0; co < CO; ++co) {
+            float acc = sBa[co];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc = fmaf(sWa[co * C + ch], p4[ch], acc);
+            a[(((size_t)n * CO + co) * h4 + by) * w4 + bx] = fmaxf(acc, 0.f);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        float s = p4[ch];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        p4[ch] = s * 0.25f;
+    }
+    if (in && (lane & 3) == 0) {
+        for (int co = 0; co < CO; ++co) {
+            float acc = sBc[co];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc = fmaf(sWc[co * C + ch], p4[ch], acc);
+            c[(((size_t)n * CO + co) * h8 + cy) * w8 + cell] = fmaxf(acc, 0.f);
+        }
+    }
+}
+
+template <int C, int CO>
+static int launch_context_pool(const float* x, const float* wa, const float* ba, const float* wc, const float* bc,
+                               float* a, float* c, int N, int h, int w, cudaStream_t st) {
+    const int w8 = w / 8;
+    dim3 grid((w8 + 31) / 32, h / 8, N);
+    context_pool_kernel<C, CO><<<grid, 128, 0, st>>>(x, wa, ba, wc, bc, a, c, h, w);
+    ADAMVS_LAUNCH_RESULT();
+}
+
+extern "C" int adamvs_context_pool_supported(int C, int CO) {
+    return (C == 32 && CO == 16) || (C == 16 && CO == 8) || (C == 8 && CO == 4);
+}
+
+extern "C" int adamvs_context_pool_f32(const float* x, const float* wa, const float* ba, const float* wc, const float* bc,
+                                       float* a, float* c, int N, int C, int CO, int h, int w, void* stream) {
+    ADAMVS_CHECK_ARG(x && wa && ba && wc && bc && a && c && N > 0 && N <= 65535 && h > 0 && w > 0 && h % 8 == 0 && w % 8 == 0);
+    ADAMVS_CHECK_ARG(h / 8 <= 65535 && adamvs_context_pool_supported(C, CO) && reinterpret_cast<uintptr_t>(x) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (CIN == 32) return launch_deconv<32, 16>(in, wpk, bias, relu, out, N, hin, win, st);
-    if (CIN == 16) return launch_deconv<16, 8>(in, wpk, bias, relu, out, N, hin, win, st);
-    return launch_deconv<48, 48>(in, wpk, bias, relu, out, N, hin, win, st);
+    if (C == 32) return launch_context_pool<32, 16>(x, wa, ba, wc, bc, a, c, N, h, w, st);
+    if (C == 16) return launch_context_pool<16, 8>(x, wa, ba, wc, bc, a, c, N, h, w, st);
+    return launch_context_pool<8, 4>(x, wa, ba, wc, bc, a, c, N, h, w, st);
 }
 
 extern "C" int adamvs_context_head_supported(int CX, int CCTX, int COUT) {

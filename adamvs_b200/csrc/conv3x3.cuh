@@ -234,7 +234,21 @@ struct V2Cfg {
     static_assert((CHUNK_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-struct TileGrid { int tiles_x, tiles_y, ntiles; };          // ntiles = tiles_x * tiles_y * B
+// Division by a run-time constant as multiply + shift (exact for n < 2^26): the persistent kernels turn a linear tile
+// index into (item, tile row, tile column) once per tile - or per chunk - in every role, and a 32-bit integer division
+// is ~25 dependent instructions on the critical path of a warp that issues one instruction every ~5 clocks.
+struct FastDiv {
+    unsigned mul, shift, d;
+    __host__ __device__ FastDiv() : mul(0), shift(0), d(1) {}
+    __host__ explicit FastDiv(int div) : d((unsigned)div) {
+        unsigned lg = 0;
+        while ((1u << lg) < d) ++lg;
+        shift = 26 + lg;
+        mul = (unsigned)(((unsigned long long)1 << shift) / d + 1);
+    }
+    __device__ __forceinline__ int div(int n) const { return (int)(((unsigned long long)(unsigned)n * mul) >> shift); }
+};
+struct TileGrid { int tiles_x, tiles_y, ntiles; FastDiv by_x, by_item; };   // ntiles = tiles_x * tiles_y * B; divisors tiles_x, tiles_x * tiles_y
 
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
 __global__ void __launch_bounds__(V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>::NT)
@@ -275,8 +289,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     auto issue = [&](int g) {                                        // elected thread only
         const int ti = g / G::NSTEP, step = g - ti * G::NSTEP;
         const int tile = blockIdx.x + ti * gridDim.x;
-        const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
-        const int ox0 = (r % tg.tiles_x) * TW, oy0 = (r / tg.tiles_x) * TH;
+        const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
+        const int tyq = tg.by_x.div(r);
+        const int ox0 = (r - tyq * tg.tiles_x) * TW, oy0 = tyq * TH;
         const int slot = g % NSTAGE;
         fence_proxy_async();
         mbar_expect_tx(&bars[slot], G::STEP_FLOATS * 4);
@@ -405,8 +420,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
         // -------------------------------------------------------------- epilogue (float4 along x)
         const int tile = blockIdx.x + ti * gridDim.x;
-        const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
-        const int ox0 = (rr % tg.tiles_x) * TW, oy0 = (rr / tg.tiles_x) * TH;
+        const int b = tg.by_item.div(tile), rr = tile - b * tiles_per_item;
+        const int tyq = tg.by_x.div(rr);
+        const int ox0 = (rr - tyq * tg.tiles_x) * TW, oy0 = tyq * TH;
         const int co_base = cob * COB + cog * COT;
         const size_t plane = (size_t)a.hout * a.wout;
         const int ox = ox0 + PX * tx;
@@ -509,6 +525,8 @@ static cudaError_t launch_v2(ConvPlan& p, int B, cudaStream_t st) {
     p.tg.tiles_x = (p.args.wout + 31) / 32;
     p.tg.tiles_y = (p.args.hout + TH - 1) / TH;
     p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
+    if (p.tg.ntiles >= (1 << 26)) return cudaErrorInvalidValue;
+    p.tg.by_x = FastDiv(p.tg.tiles_x); p.tg.by_item = FastDiv(p.tg.tiles_x * p.tg.tiles_y);
     const int ncob = COUT / COB;
     int ctas = (sm_count() * per_sm[dev]) / ncob;
     if (ctas < 1) ctas = 1;

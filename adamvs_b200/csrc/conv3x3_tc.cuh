@@ -245,8 +245,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (g >= C::NSLOT) mbar_wait_bounded(&slot_empty[slot], ((g / C::NSLOT) - 1) & 1);
                 const int ti = g / C::NCH, c = g - ti * C::NCH;
                 const int tile = blockIdx.x + ti * gridDim.x;
-                const int b = tile / tiles_per_item, r = tile - b * tiles_per_item;
-                const int ox0 = (r % tg.tiles_x) * G::TW, oy0 = (r / tg.tiles_x) * G::TH;
+                const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
+                const int ty = tg.by_x.div(r);
+                const int ox0 = (r - ty * tg.tiles_x) * G::TW, oy0 = ty * G::TH;
                 if (C::EPI_R > 0 && c == 0) {                                  // this tile's epilogue operands
                     const int es = ti % (C::EPI_R > 0 ? C::EPI_R : 1);
                     if (ti >= C::EPI_R) mbar_wait_bounded(&e_empty[es], ((ti / (C::EPI_R > 0 ? C::EPI_R : 1)) - 1) & 1);
@@ -273,6 +274,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int g = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
+                TC_TRACE(1, g, 3);
                 if (ti >= 2) mbar_wait_bounded(&d_empty[acc], ((ti >> 1) - 1) & 1);
                 for (int c = 0; c < C::NCH; ++c, ++g) {
                     const int st = g % C::NA;
@@ -312,11 +314,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int slot = g % C::NSLOT, st = g % C::NA;
             const int ti = g / C::NCH;
             const int tile = blockIdx.x + ti * gridDim.x;
-            const int rr = tile % tiles_per_item;
-            const int ox0 = (rr % tg.tiles_x) * G::TW;
+            const int rr = tile - tg.by_item.div(tile) * tiles_per_item;
+            const int ox0 = (rr - tg.by_x.div(rr) * tg.tiles_x) * G::TW;
             const int off = (ox0 - 1) - ((ox0 - 1) & ~3);                     // column of position 0 inside the box
             if (cw == 0 && lane == 0) TC_TRACE(0, g, 0);
             mbar_wait_bounded(&slot_full[slot], (g / C::NSLOT) & 1);
+            if (cw == 0 && lane == 0) TC_TRACE(0, g, 3);
             if (g >= C::NA) mbar_wait_bounded(&a_empty[st], ((g / C::NA) - 1) & 1);
             if (cw == 0 && lane == 0) TC_TRACE(0, g, 1);
             const float* pl = reinterpret_cast<const float*>(sSlot + slot * C::SLOT_BYTES) + off + lane;
@@ -364,8 +367,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int acc = ti & 1;
             const int tile = blockIdx.x + ti * gridDim.x;
-            const int b = tile / tiles_per_item, rr = tile - b * tiles_per_item;
-            const int ox = (rr % tg.tiles_x) * G::TW + lane, oy0 = (rr / tg.tiles_x) * G::TH + quarter;
+            const int b = tg.by_item.div(tile), rr = tile - b * tiles_per_item;
+            const int ty = tg.by_x.div(rr);
+            const int ox = (rr - ty * tg.tiles_x) * G::TW + lane, oy0 = ty * G::TH + quarter;
             auto process = [&](int sI) {
                 const int gi = eset + NSET * sI;
                 const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
@@ -483,6 +487,8 @@ struct TcLayer {
         p.tg.tiles_x = (p.args.wout + G::TW - 1) / G::TW;
         p.tg.tiles_y = (p.args.hout + G::TH - 1) / G::TH;
         p.tg.ntiles = p.tg.tiles_x * p.tg.tiles_y * B;
+        if (p.tg.ntiles >= (1 << 26)) return cudaErrorInvalidValue;
+        p.tg.by_x = FastDiv(p.tg.tiles_x); p.tg.by_item = FastDiv(p.tg.tiles_x * p.tg.tiles_y);
         int ctas = sm_count();
         if (ctas > p.tg.ntiles) ctas = p.tg.ntiles;
         return launch_pdl(kern, dim3(ctas, 1, 1), dim3(tc_threads(NSET)), C::SMEM, st, p.tA, p.tB, p.tU, p.tH, p.args, p.tg);

@@ -29,6 +29,7 @@ EXPORTS = (
     "adamvs_regnet_msred_f32", "adamvs_conv3x3_supported", "adamvs_conv3x3_f32",
     "adamvs_deconv3x3_supported", "adamvs_deconv3x3_f32",
     "adamvs_context_head_supported", "adamvs_context_head_f32",
+    "adamvs_deconv3x3_res_f32", "adamvs_context_pool_supported", "adamvs_context_pool_f32",
     "adamvs_conv2d_f32", "adamvs_conv2d_wgrad_f32", "adamvs_pair_score_bwd_f32", "adamvs_fused_volume_bwd_f32",
     "adamvs_softmax_expect_f32", "adamvs_softmax_expect_bwd_f32",
 )
@@ -84,6 +85,9 @@ def lib() -> ctypes.CDLL:
         L.adamvs_context_head_supported.argtypes = [ci, ci, ci]
         L.adamvs_context_head_f32.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv3x3_f32.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, vp]
+        L.adamvs_deconv3x3_res_f32.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.adamvs_context_pool_supported.argtypes = [ci, ci]
+        L.adamvs_context_pool_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv2d_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_conv2d_wgrad_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.adamvs_pair_score_bwd_f32.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -414,16 +418,37 @@ def pack_deconv3x3_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).contiguous()
 
 
-def deconv3x3(x: torch.Tensor, wpk: torch.Tensor, bias: torch.Tensor, relu: bool):
-    """act(ConvTranspose2d(k=3, s=2, p=1, output_padding=1)(x) + bias): x [N,CIN,h,w] -> [N,COUT,2h,2w]."""
+def deconv3x3(x: torch.Tensor, wpk: torch.Tensor, bias: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None):
+    """act(ConvTranspose2d(k=3, s=2, p=1, output_padding=1)(x) + bias) [+ residual]: x [N,CIN,h,w] -> [N,COUT,2h,2w]."""
     x = _f32c(x, "x")
     N, CIN, h, w = x.shape
     COUT = wpk.shape[2]
     out = torch.empty((N, COUT, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _f32c(residual, "residual")
+        assert tuple(residual.shape) == tuple(out.shape), (residual.shape, out.shape)
     with _guard(x), _timed("deconv3x3", 1):
-        _check(lib().adamvs_deconv3x3_f32(_p(x), _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu), _p(out),
-                                          N, CIN, COUT, h, w, _stream()), "deconv3x3")
+        _check(lib().adamvs_deconv3x3_res_f32(_p(x), _p(_f32c(wpk, "wpk")), _p(_f32c(bias, "bias")), int(relu), _p(residual), _p(out),
+                                              N, CIN, COUT, h, w, _stream()), "deconv3x3")
     return out
+
+
+def context_pool_supported(c: int, co: int) -> bool:
+    return bool(lib().adamvs_context_pool_supported(int(c), int(co)))
+
+
+def context_pool(x: torch.Tensor, wa: torch.Tensor, ba: torch.Tensor, wc: torch.Tensor, bc: torch.Tensor):
+    """relu(conv1x1(avgpool4(x), wa) + ba), relu(conv1x1(avgpool8(x), wc) + bc): x [N,C,h,w]; wa, wc [CO,C(,1,1)]."""
+    x = _f32c(x, "x")
+    N, C, h, w = x.shape
+    CO = wa.shape[0]
+    a = torch.empty((N, CO, h // 4, w // 4), device=x.device, dtype=torch.float32)
+    c = torch.empty((N, CO, h // 8, w // 8), device=x.device, dtype=torch.float32)
+    with _guard(x), _timed("context_pool", 1):
+        _check(lib().adamvs_context_pool_f32(_p(x), _p(_f32c(wa.reshape(CO, C), "wa")), _p(_f32c(ba, "ba")),
+                                             _p(_f32c(wc.reshape(CO, C), "wc")), _p(_f32c(bc, "bc")), _p(a), _p(c),
+                                             N, C, CO, h, w, _stream()), "context_pool")
+    return a, c
 
 
 def polyphase_5x5_s2_weight(w: torch.Tensor) -> torch.Tensor:

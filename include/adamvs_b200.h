@@ -205,6 +205,18 @@ int adamvs_context_head_f32(const float* x, const float* ctx_a, const float* ctx
 int adamvs_deconv3x3_supported(int CIN, int COUT);
 int adamvs_deconv3x3_f32(const float* in, const float* wpk, const float* bias, int relu, float* out,
                          int N, int CIN, int COUT, int hin, int win, void* stream);
+/* The same with a skip tensor added AFTER the activation (CostRegNet2D's `e + up(y)`, adamvs.py:233-235):
+ * out = act(convT(in) + bias) + residual; residual [N,COUT,2h,2w] or NULL. */
+int adamvs_deconv3x3_res_f32(const float* in, const float* wpk, const float* bias, int relu, const float* residual,
+                             float* out, int N, int CIN, int COUT, int hin, int win, void* stream);
+
+/* The two pooled-context branches in front of a FeatureNet0 output head (adamvs.py:112-147): AvgPool2d(4) / AvgPool2d(8)
+ * -> 1x1 conv -> eval-mode BatchNorm (folded into wa/ba, wc/bc by the caller) -> ReLU, one pass over x.
+ * x [N,C,h,w] (h, w multiples of 8); wa, wc [CO,C]; a [N,CO,h/4,w/4]; c [N,CO,h/8,w/8]. */
+int adamvs_context_pool_supported(int C, int CO);
+int adamvs_context_pool_f32(const float* x, const float* wa, const float* ba, const float* wc, const float* bc,
+                            float* a, float* c, int N, int C, int CO, int h, int w, void* stream);
+
 
 /* ---- Training path: backward kernels, csrc/train.cu ------------------------------------------- */
 

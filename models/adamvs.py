@@ -77,18 +77,22 @@ def _conv_mode(conv):
     return None
 
 
-def _native_conv(x, x2, wpk, b, mode, c, relu):
-    """Run one folded conv on the C-ABI kernels; None when this channel combination has no kernel."""
+def _native_conv(x, x2, wpk, b, mode, c, relu, residual=None):
+    """Run one folded conv on the C-ABI kernels; None when this channel combination has no kernel.
+    `residual` (transposed convs only) is added after the activation."""
     if mode == "deconv":
         if x2 is None and _ops.deconv3x3_supported(x.shape[1], wpk.shape[2]):
-            return _ops.deconv3x3(x, wpk, b, relu)
+            return _ops.deconv3x3(x, wpk, b, relu, residual)
         return None
     if mode == "poly":
         if x2 is None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and _ops.conv3x3_supported(4 * x.shape[1], 0, wpk.shape[2], 1):
             return _ops.conv3x3(F.pixel_unshuffle(x, 2), None, wpk, b, relu, 1)
         return None
     stride = c.stride[0]
-    if x2 is None and x.shape[1] < 8 and wpk.shape[0] == 8:           # 3-channel image: zero-padded to one 8-channel chunk
+    if x2 is None and x.shape[1] == 3 and wpk.shape[0] == 8 and stride == 1 and x.shape[3] % 4 == 0 and x.is_contiguous() \
+            and x.data_ptr() % 16 == 0 and _ops.conv3x3_supported(3, 0, wpk.shape[2], 1):
+        return _ops.conv3x3(x, None, wpk, b, relu, 1)                 # the image is read in place: rows 3..7 of wpk are zero
+    if x2 is None and x.shape[1] < 8 and wpk.shape[0] == 8:           # other narrow inputs: zero-padded to one 8-channel chunk
         x = F.pad(x, (0, 0, 0, 0, 0, 8 - x.shape[1]))
     if _ops.conv3x3_supported(x.shape[1], 0 if x2 is None else x2.shape[1], wpk.shape[2], stride):
         return _ops.conv3x3(x, x2, wpk, b, relu, stride)
@@ -172,6 +176,13 @@ class FeatureNet0(nn.Module):
                 and _ops.context_head_supported(x.shape[1], br_a[1].conv.out_channels, proj.out_channels)):
             # both upsamplings, the concatenation and the 1x1 projection in one pass over x (adamvs_context_head_f32);
             # the 8x8 average is taken from the 4x4 averages (one read of x instead of two; a mean of equal-sized means)
+            if ((br_a[0].kernel_size, br_b[0].kernel_size) == ((4, 4), (8, 8)) and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0
+                    and _ops.context_pool_supported(x.shape[1], br_a[1].conv.out_channels)):
+                # pooling + 1x1 conv + folded BatchNorm + ReLU of both branches in one pass too (adamvs_context_pool_f32)
+                wa, ba, _, _ = _folded(br_a[1].conv, br_a[1].bn)
+                wc, bc, _, _ = _folded(br_b[1].conv, br_b[1].bn)
+                ca, cc = _ops.context_pool(x, wa, ba, wc, bc)
+                return _ops.context_head(x, ca, cc, proj.weight)
             pa = br_a[0](x)
             pb = F.avg_pool2d(pa, 2) if (br_a[0].kernel_size, br_b[0].kernel_size) == ((4, 4), (8, 8)) else br_b[0](x)
             return _ops.context_head(x, br_a[1](pa), br_b[1](pb), proj.weight)
@@ -205,25 +216,26 @@ class CostRegNet2D(nn.Module):
                 nn.BatchNorm2d(n), nn.ReLU(inplace=True)))
         self.prob = nn.Conv2d(n, n, 3, stride=1, padding=1)
 
-    def _up(self, seq, x):
+    def _up(self, seq, x, skip):
+        """skip + relu(bn(convT(x))): the skip addition rides in the native kernel's epilogue."""
         if self.training or not _FOLD_BN:
-            return seq(x)
+            return skip + seq(x)
         c = seq[0]
         w, b, wpk, mode = _folded(c, seq[1])
         if mode is not None and _NATIVE_CONV and x.is_cuda and x.dtype == torch.float32:
-            y = _native_conv(x, None, wpk, b, mode, c, True)
+            y = _native_conv(x, None, wpk, b, mode, c, True, residual=skip)
             if y is not None:
                 return y
-        return F.relu_(F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation))
+        return skip + F.relu_(F.conv_transpose2d(x, w, b, c.stride, c.padding, c.output_padding, c.groups, c.dilation))
 
     def forward(self, x):
         e0 = self.conv0(x)
         e2 = self.conv2(self.conv1(e0))
         e4 = self.conv4(self.conv3(e2))
         y = self.conv6(self.conv5(e4))
-        y = e4 + self._up(self.conv7, y)
-        y = e2 + self._up(self.conv9, y)
-        y = e0 + self._up(self.conv11, y)
+        y = self._up(self.conv7, y, e4)
+        y = self._up(self.conv9, y, e2)
+        y = self._up(self.conv11, y, e0)
         if not self.training and _NATIVE_CONV and y.is_cuda and y.dtype == torch.float32:
             w, b, wpk, mode = _folded(self.prob, None)
             out = _native_conv(y, None, wpk, b, mode, self.prob, False) if mode is not None else None

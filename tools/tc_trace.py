@@ -15,7 +15,7 @@ from tools.tc_regnet_check import NAMES
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--tf32", action="store_true")
     a = ap.parse_args()
     sd = synth.fill_state_dict(synth.state_dict_shapes(8), 21)
@@ -50,8 +50,12 @@ def main():
         print(f"{t:4d} | {e[0]:8d} {e[1]:8d} {e[2]:8d} | step0: tmem {x[0]:8d} math {x[1]:8d} stored {x[2]:8d}")
     if n > 8:
         print("steady state clk/chunk (mma issued):", (int(mma[n - 1, 2]) - int(mma[4, 2])) / (n - 5))
-        d_wait = (conv[5:n, 1] - conv[5:n, 0]).mean(); d_store = (conv[5:n, 2] - conv[5:n, 1]).mean(); d_fetch = (conv[5:n, 3] - conv[5:n, 2]).mean()
-        print(f"converter: wait stage {d_wait:.0f}, split+store {d_store:.0f}, fetch issue {d_fetch:.0f}")
+        d_slot = (conv[5:n, 3] - conv[5:n, 0]).mean(); d_stage = (conv[5:n, 1] - conv[5:n, 3]).mean(); d_store = (conv[5:n, 2] - conv[5:n, 1]).mean()
+        gap = (conv[6:n, 0] - conv[5:n - 1, 2]).mean()
+        print(f"converter: wait TMA slot {d_slot:.0f}, wait operand stage free {d_stage:.0f}, split+store {d_store:.0f}, loop gap {gap:.0f}")
+        first = mma[0:n:2]                       # first chunk of a tile carries the accumulator wait stamp (gates1: 2 chunks per tile)
+        d_acc = (first[3:, 0] - first[3:, 3]).mean()
+        print(f"mma thread: wait accumulator free (per tile) {d_acc:.0f}")
         m_wait = (mma[5:n, 1] - mma[5:n, 0]).mean(); m_issue = (mma[5:n, 2] - mma[5:n, 1]).mean()
         print(f"mma thread: wait full {m_wait:.0f}, issue {m_issue:.0f}")
         e_wait = (epi[2:nt, 1] - epi[2:nt, 0]).mean(); e_run = (epi[2:nt, 2] - epi[2:nt, 1]).mean()
