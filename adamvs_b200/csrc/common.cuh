@@ -65,8 +65,10 @@ __device__ __forceinline__ Ray make_ray(const float* __restrict__ P, float x, fl
 
 // Bilinear tap set with per-corner zero padding (grid_sample, padding_mode='zeros',
 // align_corners=True).  Offsets are clamped into the image so that a load is always
-// legal; out-of-image corners carry weight 0.  Non-finite coordinates or Z<=0 give all-zero weights
-// (the reference's behaviour there is platform dependent — documented deviation).
+// legal; out-of-image corners carry weight 0.  A sample behind the source camera (finite Z < 0) is treated as the
+// reference treats it: X/Z, Y/Z are taken as they come and sampled where they land (models/module.py:553-556 has
+// no sign test).  Only non-finite coordinates (Z = 0, NaN inputs), for which the reference's grid_sample result is
+// platform dependent (NaN on CPU), give all-zero weights here — the one documented deviation.
 struct Taps {
     int o00, o01, o10, o11;   // y*w+x offsets
     float w00, w01, w10, w11;
@@ -79,7 +81,7 @@ __device__ __forceinline__ Taps make_taps(const Ray& r, float d, int h, int w) {
     float u = __fdiv_rn(X, Z);
     float v = __fdiv_rn(Y, Z);
     Taps t;
-    const bool ok = (Z > 0.f) && (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);  // false for NaN
+    const bool ok = (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);      // false for NaN / inf
     if (!ok) { u = -2.f; v = -2.f; }
     const float fu = floorf(u), fv = floorf(v);
     const int x0 = (int)fu, y0 = (int)fv;

@@ -207,7 +207,7 @@ struct WarpVolArgs {
 };
 
 // Unclamped bilinear cell (x0,y0 may be -1) and corner weights; false when the sample lies entirely
-// outside the source image, behind the camera or is not finite (contributes zero).
+// outside the source image or is not finite (contributes zero).
 __device__ __forceinline__ bool cell_taps(const Ray& r, float d, int h, int w, float scale, int& x0, int& y0, float (&wt)[4]) {
     const float X = __fadd_rn(__fmul_rn(r.qx, d), r.tx);
     const float Y = __fadd_rn(__fmul_rn(r.qy, d), r.ty);
@@ -219,7 +219,7 @@ __device__ __forceinline__ bool cell_taps(const Ray& r, float d, int h, int w, f
     // imitated here.
     const float u = __fdiv_rn(X, Z);
     const float v = __fdiv_rn(Y, Z);
-    const bool ok = (Z > 0.f) && (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);
+    const bool ok = (u > -1.f) && (u < (float)w) && (v > -1.f) && (v < (float)h);      // false for NaN / inf; finite Z < 0 as the reference
     const float fu = floorf(ok ? u : 0.f), fv = floorf(ok ? v : 0.f);
     x0 = (int)fu; y0 = (int)fv;
     const float ax = (ok ? u : 0.f) - fu, ay = (ok ? v : 0.f) - fv;

@@ -1,14 +1,16 @@
 """Drop-in replacement for the reference's ``models/adamvs.py`` — same importable names, constructor
 signatures, ``state_dict`` keys/shapes and forward contract
 (``imgs, proj_matrices, depth_values -> {"stage1..3": {...}, "depth", "photometric_confidence", ...}``),
-so the reference's ``train_whu.py`` (test/profile) and ``predict_whu.py`` run against it unchanged
-(reference: models/adamvs.py:316-396 AdaMVSNet, :537-620 Infer_AdaMVSNet, :8-46 cas_mvs_vis_loss).
+so the reference's ``train_whu.py`` (train / test / profile) and ``predict_whu.py`` run against it unchanged
+(reference: models/adamvs.py:316-396 AdaMVSNet, :537-620 Infer_AdaMVSNet, :8-46 cas_mvs_vis_loss; proven by
+tests/test_reference_scripts.py, which executes the unmodified scripts).
 
 The modules below only *hold parameters* in the reference's tree; the cascade cost-volume hot path
 (warp + cost volume, recurrent regulariser, regression, hypothesis narrowing) runs in the sm_100a
-kernels of ``adamvs_b200`` via ``adamvs_b200.cascade``.  FeatureNet0 and the stage-1 pair U-Net
-(CostRegNet2D) are outside that path and run as true-fp32 cuDNN convolutions.
-There is no CPU fallback: forward() on CPU tensors raises.
+kernels of ``adamvs_b200`` via ``adamvs_b200.cascade`` (inference) and ``adamvs_b200.autograd`` (model.train():
+the same ops with their backward kernels).  In eval mode FeatureNet0 and the stage-1 pair U-Net (CostRegNet2D,
+SURVEY.md §8f-1) run on the same native convolution kernels with BatchNorm folded; under model.train() they are
+torch modules (batch-statistics BatchNorm, cuDNN in true fp32).  There is no CPU fallback: forward() on CPU tensors raises.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ import torch.nn.functional as F
 from adamvs_b200 import cascade as _cascade
 from adamvs_b200 import ops as _ops
 
-__all__ = ["AdaMVSNet", "Infer_AdaMVSNet", "cas_mvs_vis_loss", "FeatureNet0", "CostRegNet2D"]
+__all__ = ["AdaMVSNet", "Infer_AdaMVSNet", "cas_mvs_vis_loss", "FeatureNet0", "CostRegNet2D", "invalidate_folded"]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -99,9 +101,18 @@ def _native_conv(x, x2, wpk, b, mode, c, relu, residual=None):
     return None
 
 
+def invalidate_folded(module: nn.Module) -> None:
+    """Drop every cached BatchNorm fold below `module`.  The cache key is (data_ptr, _version) of the tensors involved,
+    which in-place tensor methods, load_state_dict, optimiser steps and .to() all change; writes through `.data`
+    (`p.data.copy_(...)`) bypass the version counter - call this after such writes."""
+    for m in module.modules():
+        m.__dict__.pop("_adamvs_folded", None)
+
+
 def _folded(conv, bn):
     """(weight, bias, packed weight | None, native mode | None) of conv followed by eval-mode BatchNorm (bn may be None:
-    plain conv with bias), cached on the conv module and rebuilt whenever a tensor involved is modified or moved."""
+    plain conv with bias), cached on the conv module and rebuilt whenever a tensor involved is modified or moved
+    (see invalidate_folded for the one exception)."""
     src = (conv.weight,) + ((bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else (conv.bias,))
     key = tuple((t.data_ptr(), t._version) for t in src)
     cache = conv.__dict__.get("_adamvs_folded")

@@ -147,7 +147,9 @@ def test_cost_volume_fallback_paths_vs_oracle(case):
 
 
 def test_fused_volume_zero_padding_and_behind_camera():
-    """Out-of-image taps contribute zero per corner (grid_sample zeros padding); Z<=0 gives zeros."""
+    """Out-of-image taps contribute zero per corner (grid_sample zeros padding); a source camera that looks the other
+    way (finite Z < 0 everywhere) is sampled at the mirrored coordinates X/Z, Y/Z exactly as the reference does
+    (models/module.py:553-556 has no sign test) - compared against the oracle, not against zeros."""
     ops = _ops()
     B, V, C, D, h, w = 1, 2, 8, 2, 8, 12
     feat = torch.ones(B, V, C, h, w)
@@ -162,10 +164,15 @@ def test_fused_volume_zero_padding_and_behind_camera():
                            ops.EPS_DENOMINATOR, D).cpu() * (1 + 1e-5)
     assert abs_err(got, want) < 1e-5
     assert abs(float(want[0, 0, 0, 0, w - 6]) - 0.5) < 1e-4 and float(want[0, 0, 0, 0, w - 5]) == 0.0
-    proj[0, 1, 2, 2] = -1.0                  # source camera looks the other way: Z < 0 everywhere
+    proj[0, 1, 2, 2] = -1.0                  # source camera looks the other way: Z = -600 everywhere
+    proj[0, 1, 0, 3] = -9.0 * 600.0          # u = (x*d - 5400) / -d = 9 - x: columns 0..9 land inside the 12-wide image, mirrored
+    proj[0, 1, 1, 1] = -1.0                  # v = (-y*d) / -d = y
+    ramp = torch.arange(w, dtype=torch.float32).repeat(B, V, C, h, 1) + 1.0
     relproj, _ = ops.cascade_prepare([proj.to(_dev())] * 3, dv.to(_dev()), ops.INTERVAL_FROM_RANGE, 1, [D] * 3, [1.0] * 3)
-    got = ops.fused_volume(feat.to(_dev()), relproj[0], hyp, torch.ones(B, 1, h, w, device=_dev()), ops.EPS_DENOMINATOR, D)
-    assert float(got.abs().max()) == 0.0
+    want = O.homography_warp(ramp[:, 1], proj[:, 1], proj[:, 0], hyps) * ramp[:, 0].unsqueeze(2)
+    got = ops.fused_volume(ramp.to(_dev()), relproj[0], hyp, torch.ones(B, 1, h, w, device=_dev()), ops.EPS_DENOMINATOR, D).cpu() * (1 + 1e-5)
+    assert float(want.abs().max()) > 20.0 and float(want[0, 0, 0, 0, 11]) == 0.0       # mirrored ramp inside, zero where u < 0
+    assert abs_err(got, want) < 2e-4 * float(want.abs().max())
 
 
 @pytest.mark.parametrize("C,D,h,w,up,prob", [(32, 6, 16, 24, True, "softmax"), (16, 4, 32, 48, True, "exp"),

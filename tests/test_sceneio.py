@@ -90,19 +90,3 @@ def test_center_images_matches_numpy_definition():
     want = (f - f.mean(axis=(1, 2), keepdims=True)) / (np.sqrt(f.var(axis=(1, 2), keepdims=True)) + 0.00000001)
     assert got.shape == (2, 3, 24, 40)
     assert float(np.abs(got - want.transpose(0, 3, 1, 2)).max()) < 2e-5
-
-
-def test_predict_cli_builds_the_reference_modules_and_refuses_cpu(tmp_path):
-    from adamvs_b200 import predict
-    a = predict.build_parser().parse_args(["--data_folder", SCENE, "--output_folder", str(tmp_path), "--ndepths", "8,4,2",
-                                           "--numdepth", "32", "--view_num", "3"])
-    assert (a.model, a.batch_size, a.depth_inter_r, a.cr_base_chs) == ("adamvs", 8, "4,2,1", "8,8,8")
-    m = predict.model_from_args(a)
-    assert type(m).__name__ == "Infer_AdaMVSNet" and len(m.state_dict()) > 200
-    a.model = "msrednet"
-    assert type(predict.model_from_args(a)).__name__ == "Infer_CascadeREDNet"
-    if not torch.cuda.is_available():
-        with pytest.raises(SystemExit):
-            predict.main(["--data_folder", SCENE, "--output_folder", str(tmp_path)])
-    with pytest.raises(SystemExit):
-        predict.main(["--data_folder", SCENE, "--output_folder", str(tmp_path), "--resize_scale", "0.5"])
