@@ -116,10 +116,14 @@ __device__ __forceinline__ Lerp lerp_index(int dst, float scale, int n_in) {
     return r;
 }
 
-// Gate non-linearities on the SFU (MUFU.EX2 + MUFU.RCP): absolute error ~1e-7 on values in [0,1] / [-1,1], far below the
-// parity bar, at a quarter of the instructions of expf + IEEE division / tanhf (they run 64x per thread per tile in the
-// GRU epilogues).  Saturation: __expf -> inf gives __fdividef -> 0.
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+// Gate non-linearities on the SFU: exactly one MUFU.EX2 and one MUFU.RCP each (ex2.approx.ftz / rcp.approx.ftz through
+// inline PTX).  __expf / __fdividef compile to the same two MUFU operations plus a denormal-range guard (FSETP + two
+// predicated FMULs per exp) that the gates do not need - flushing exp(-x) < 2^-126 to zero gives sigmoid = 1, tanh = +-1
+// exactly as the limit does - and that was a sixth of the GRU epilogue's instructions (they run 64x per thread per tile).
+// Absolute error ~1e-7 on values in [0,1] / [-1,1], far below the parity bar.  Saturation: ex2 -> +inf gives rcp -> 0.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_f(float x) { return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz(2.8853900817779268f * x)), 1.f); }
 
 }  // namespace adamvs

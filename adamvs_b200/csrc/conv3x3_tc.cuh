@@ -403,12 +403,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // and the compiler will not move such a load above an earlier global store - with load, MUFU and store
                 // interleaved per channel the eight ~180-clk dependency chains ran one after the other (profiles/r02e).
                 float res[CG];
+                static_assert(EPI != EPI_GATES || HC % CG == 0, "a step's channel group lies in one gate half");
+                const bool reset_half = c0 < HC;                             // warp-uniform: the whole step is reset or update gates
 #pragma unroll
                 for (int c = 0; c < CG; ++c) {
                     const int co = c0 + c;
                     if (EPI == EPI_GATES) {
                         const float s = sigmoid_f(v[c] + sBias[co]);
-                        res[c] = co < HC ? s * opnd[(co < HC ? co : 0) * C::EPI_PLANE] : s;      // reset gate -> r*h | update gate
+                        res[c] = reset_half ? s * opnd[(reset_half ? co : 0) * C::EPI_PLANE] : s;   // reset gate -> r*h | update gate
                     } else if (EPI == EPI_CAND) {
                         const float u = opnd[co * C::EPI_PLANE], hv = opnd[(COUT + co) * C::EPI_PLANE];
                         res[c] = u * hv + (1.f - u) * tanh_f(v[c] + sBias[co]);
