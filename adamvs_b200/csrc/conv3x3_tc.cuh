@@ -171,7 +171,8 @@ struct TcCfg {
 // NSET = 2 / 3 / 4 (512 / 640 / 768 threads, no spills) give K3 stage 1/2/3 = 10.97/21.83/19.61, 10.94/22.08/19.84,
 // 10.97/22.28/20.05 ms - no gain, so the epilogue's warp count is not what bounds these kernels; 2 sets stay.
 constexpr int kTcDefaultSets = 2;
-constexpr int tc_threads(int nset) { return (12 + 4 * (nset - 1)) * 32; }
+constexpr int kTcConverters = 4;                              // converter warps 4-7; 8 (adding warps 16-19, a 640-thread CTA) measured 1.7 % SLOWER (profiles/r2d)
+constexpr int tc_threads(int nset) { return (12 + 4 * (nset - 1) + (kTcConverters > 4 ? 4 : 0)) * 32; }
 
 template <int CA, int CB, int COUT, int EPI, int MT, int PREC, int NSET>
 __global__ void __launch_bounds__(tc_threads(NSET), 1)
@@ -203,8 +204,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
-        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], kTcConverters); }
+        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], kTcConverters); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4 * NSET); }
         for (int i = 0; i < 3; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 4 * NSET); }
         fence_mbar_init();
@@ -305,10 +306,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 umma_commit(&d_full[acc]);                                     // accumulator complete
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if ((warp >= 4 && warp < 8) || (kTcConverters > 4 && warp >= 12 + 4 * (NSET - 1))) {
         // ===== converters: planar TMA slot -> hi/lo quad-interleaved operand stage; warp cw converts rows cw, cw+4, ...
-        const int cw = warp - 4;
-        constexpr int NJ = (G::IH + 3) / 4;
+        const int cw = warp < 8 ? warp - 4 : warp - (12 + 4 * (NSET - 1)) + 4;
+        constexpr int NJ = (G::IH + kTcConverters - 1) / kTcConverters;
 #pragma unroll 1
         for (int g = 0; g < total; ++g) {
             const int slot = g % C::NSLOT, st = g % C::NA;
@@ -328,14 +329,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float e[NJ][CK];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                const int r = cw + 4 * j;
+                const int r = cw + kTcConverters * j;
                 const bool on = j < NJ - 1 || r < G::IH;                       // warp-uniform
 #pragma unroll
                 for (int ch = 0; ch < CK; ++ch) e[j][ch] = on ? pl[(ch * G::IH + (on ? r : 0)) * G::BOXW] : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                const int r = cw + 4 * j;
+                const int r = cw + kTcConverters * j;
                 if (j == NJ - 1 && r >= G::IH) break;                          // warp-uniform
                 const int pos = r * G::PW + lane;
 #pragma unroll
@@ -353,7 +354,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) { mbar_arrive(&a_full[st]); mbar_arrive(&slot_empty[slot]); }
             if (cw == 0 && lane == 0) TC_TRACE(0, g, 2);
         }
-    } else if (warp < 4 || warp >= 12) {
+    } else if (warp < 4 || (warp >= 12 && warp < 12 + 4 * (NSET - 1))) {
         // ===== epilogue (TMEM lane quarter = warp % 4 = image row mt*4 + quarter): runs one tile behind the MMAs.  One warp
         // per scheduler is latency bound (TMEM load -> shuffles -> MUFU -> stores: ~4.4 clk per instruction measured),
         // so two warps per quarter take alternate (M tile, channel group) steps.

@@ -9,7 +9,9 @@
 // stride-1 convolutions run on tcgen05 with an exact hi/lo tf32 operand split (conv3x3_tc.cuh) when the plane is large
 // enough, else - like conv2 and the tail always - on register-tiled FFMA kernels (conv3x3.cuh): DESIGN.md §3.
 //
-// Per depth plane (all on one stream, states/intermediates stay L2-resident):
+// Per depth plane (all on one stream; at the bench batch every intermediate is far larger than the L2 - 300 MB per 8-channel
+// tensor at stage 3, B = 32 - and is re-read from HBM by the next kernel, which measurements show is NOT what bounds the
+// chain: DESIGN.md 3, "Round 2: what bounds these kernels"):
 //   1 conv1   x1  = relu(conv3x3(F_k))                                  C  -> 8
 //   2 gates1  r,u = sigmoid(conv3x3(cat(x1,h1)) + b);  rh1 = r*h1        16 -> 16
 //   3 cand1   h1  = u*h1 + (1-u)*tanh(conv3x3(cat(x1,rh1)) + b)          16 -> 8

@@ -5,7 +5,8 @@ importable names (``CascadeREDNet``, ``Infer_CascadeREDNet``, ``cas_rednet_loss`
 
 The modules below only hold parameters; the variance cost volume, the four-level GroupNorm conv-GRU
 regulariser and the regression run in the sm_100a kernels of ``adamvs_b200`` (K5/K6) via
-``adamvs_b200.cascade_msred``.  ``FeatureNet`` (outside the path) runs as true-fp32 cuDNN convolutions.
+``adamvs_b200.cascade_msred``.  ``FeatureNet`` (outside the path) runs on the native
+convolution kernels where its layer shapes have one (``adamvs_conv3x3_f32``), else as true-fp32 cuDNN convolutions.
 """
 from __future__ import annotations
 

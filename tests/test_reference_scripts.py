@@ -24,16 +24,16 @@ def _state_dict():
     return synth.fill_state_dict(synth.state_dict_shapes(NDEPTHS[0]), 5)
 
 
-def _run_script(tmp, models, extra_env=None, cpu_shim=False):
+def _run_script(tmp, models, extra_env=None, cpu_shim=False, model="adamvs", sd=None):
     from tools.run_reference_script import make_checkpoint
-    ck = os.path.join(tmp, "model.ckpt")
-    make_checkpoint(ck, _state_dict())
-    out = os.path.join(tmp, "out_" + models)
+    ck = os.path.join(tmp, f"model_{model}.ckpt")
+    make_checkpoint(ck, _state_dict() if sd is None else sd)
+    out = os.path.join(tmp, f"out_{model}_{models}")
     os.makedirs(out, exist_ok=True)
     cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), "--script", "predict_whu.py", "--models", models]
     if cpu_shim:
         cmd.append("--cpu-shim")
-    cmd += ["--", "--model", "adamvs", "--data_folder", SCENE, "--output_folder", out, "--loadckpt", ck,
+    cmd += ["--", "--model", model, "--data_folder", SCENE, "--output_folder", out, "--loadckpt", ck,
             "--view_num", str(VIEWS), "--numdepth", str(NUM_DEPTH), "--ndepths", ",".join(map(str, NDEPTHS)),
             "--max_h", str(MAX_H), "--max_w", str(MAX_W), "--resize_scale", "1"]
     env = dict(os.environ, **(extra_env or {}))
@@ -110,6 +110,24 @@ def test_reference_predict_script_runs_unchanged_on_the_dropin(tmp_path):
         assert rel_err(torch.from_numpy(mine[k][0]), torch.from_numpy(ours[k][0])) < 1e-5, k
         assert abs_err(torch.from_numpy(mine[k][1]), torch.from_numpy(ours[k][1])) < 1e-5, k
         assert mine[k][2] == ours[k][2], k
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_predict_script_runs_unchanged_on_the_msrednet_dropin(tmp_path):
+    """The same for `--model msrednet` (BASELINE configs[4]'s class, Infer_CascadeREDNet): the unmodified predict_whu.py
+    with this repo's models/msrednet.py against the same script with the reference's own module on this GPU in true fp32.
+    MS-REDNet's probabilities carry the reference's own arithmetic noise (5e-4 at these sizes), hence 2e-3."""
+    sd = synth.fill_state_dict(synth.msred_state_dict_shapes(), 41)
+    ours_dir, log = _run_script(str(tmp_path), "ours", model="msrednet", sd=sd)
+    assert os.path.join(ROOT, "models") in log
+    ref_dir, _ = _run_script(str(tmp_path), "reference", extra_env={"NVIDIA_TF32_OVERRIDE": "0"}, model="msrednet", sd=sd)
+    ours, ref = _outputs(ours_dir), _outputs(ref_dir)
+    assert sorted(ours) == sorted(ref) and len(ours) == 3
+    for k in ours:
+        assert rel_err(torch.from_numpy(ours[k][0]), torch.from_numpy(ref[k][0])) < 1e-4, k
+        assert abs_err(torch.from_numpy(ours[k][1]), torch.from_numpy(ref[k][1])) < 2e-3, k
+        assert ours[k][2] == ref[k][2], k
 
 
 @needs_ref
