@@ -321,6 +321,30 @@ def test_forward_full_size_vs_oracle(cls):
     assert float(want["stage3"]["photometric_confidence"].max()) > 0.5
 
 
+@pytest.mark.parametrize("V", [2, 3, 4, 7])
+@pytest.mark.parametrize("cls", ["whole", "stream"])
+def test_forward_other_view_counts_vs_oracle(V, cls):
+    """`--view_num` is a run-time choice in the reference's scripts (predict_whu.py:33): 1, 2, 3 and 6 source views
+    (the kernels are instantiated for 1..6) through the whole forward against the oracle, both classes."""
+    from adamvs_b200 import synth
+    nd = (8, 4, 2)
+    imgs, proj, dv2 = synth.make_sample(1, 64, 96, V, seed=50 + V)
+    dv3 = torch.cat([dv2, torch.full((1, 1), (synth.DEPTH_MAX - synth.DEPTH_MIN) / 32)], 1)
+    sd = synth.fill_state_dict(synth.state_dict_shapes(nd[0]), 60 + V)
+    f = O.feature_net(sd, imgs[:, 0])
+    sd = synth.calibrate_state_dict(sd, {k: float(f[k].std()) for k in f}, 20.0)
+    if cls == "whole":
+        want = O.adamvs_forward(sd, imgs, proj, dv3, ndepths=nd)
+    else:
+        want = O.infer_adamvs_forward(sd, imgs, proj, dv2, num_depth=32, ndepths=nd)
+    m = _model(cls, sd, nd, 32)
+    out = m(imgs.to(_dev()), _to_dev(proj), (dv3 if cls == "whole" else dv2).to(_dev()))
+    for s in ("stage1", "stage2", "stage3"):
+        _compare_outputs(out[s], want[s]["depth"], want[s]["photometric_confidence"], f"V={V}/{cls}/{s}")
+        assert len(out[s]["pair_confidence"]) >= V - 1
+    assert len(out["stage1"]["pair_result"]) == V - 1
+
+
 def test_forward_tf32_math_within_its_own_stated_tolerance():
     """The reduced-precision variant (bench.py --math tf32: K3's activations rounded to tf32 in one pass, weights still
     split exactly) is reported separately with ITS OWN tolerance: depth 5e-3 relative, probability 3e-2
