@@ -192,6 +192,216 @@ tail_regress_kernel(const float* h2s, const float* __restrict__ wpk_up, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same tail, TMA-fed and persistent (w % 8 == 0).  The kernel above spends most of a tile waiting: h2 patch from
+// global -> barrier -> skip connection from global -> FFMA -> barrier -> output layer, with 60-70 % of the threads of a
+// 3-CTA SM idle in the first phase (FFMA pipe 18 % busy, 8.9 kclk per tile and SM against ~3.2 kclk of issue slots).
+// Here a CTA walks over tiles; one thread requests the NEXT tile's two boxes (h2 patch, h1 = skip connection over the
+// quads' whole footprint, image borders zero-filled by the tensor map) while the CTA computes the current one, y is
+// written in place over the h1 box (every element is read and written by the one thread that owns its quad), and the
+// output layer runs with lanes along x (conflict-free rows, 128 / 256-byte row stores).  Same arithmetic, same order of
+// the FFMA chains: bit-identical logits.
+// ------------------------------------------------------------------------------------------------
+template <bool UP, int TH>
+struct TailTma {
+    static constexpr int LO = UP ? 0 : 1;
+    static constexpr int QH = TH / 2 + 1 + LO, QW = kTailW / 2 + 1 + LO;          // quads (rows x cols)
+    // TMA boxes start on 16-byte boundaries of the global rows: the quads of the stage-3 form begin one quad left of the
+    // tile (x = 16t - 1 at half, 32t - 2 at full resolution), so its boxes begin 3 / 2 columns further left
+    static constexpr int XH = UP ? 0 : 3, XY = UP ? 0 : 2;                         // first used column of the h2 / h1 box
+    static constexpr int YH = 2 * QH, YP = UP ? 36 : 40;                           // y / h1 box: rows, pitch (XY + 2*QW <= YP)
+    static constexpr int HH = QH + 1, HP = UP ? 20 : 24;                           // h2 box: rows, pitch (XH + QW + 1 <= HP)
+    static constexpr int H2F = 16 * HH * HP, H1F = 8 * YH * YP, STAGE = H2F + H1F; // floats; both multiples of 32
+    static constexpr int R = TH / 8;                                               // output rows per thread (8 warps)
+    static constexpr size_t SMEM = sizeof(float) * (2 * STAGE + 16 * 72 + 8 * 3 * 4 + 4) + 2 * sizeof(uint64_t);
+    static_assert(QH * QW <= 256 && TH % 8 == 0 && XY + 2 * QW <= YP && XH + QW + 1 <= HP, "tile geometry");
+    static_assert(2 * SMEM + 2048 <= 227 * 1024, "two CTAs per SM");
+    static_assert((H2F * 4) % 128 == 0 && (H1F * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
+};
+
+template <bool UP, int TH>
+__global__ void __launch_bounds__(256, 2)
+tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ CUtensorMap tmH1,
+                const float* __restrict__ wpk_up, const float* __restrict__ up_b, OutWeights ow,
+                float* __restrict__ logits, int k, int D, int h, int w, TileGrid tg) {
+    using G = TailTma<UP, TH>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sIn = reinterpret_cast<float*>(smem_raw);               // [2][h2 box | h1 box]
+    float* sWu = sIn + 2 * G::STAGE;                               // [16][9][8]
+    float* sWo = sWu + 16 * 72;                                    // [8][3][4] (kx padded), then the bias
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sWo + 8 * 3 * 4 + 4);
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const size_t hw = (size_t)h * w;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    pdl_launch_dependents();
+    for (int i = tid; i < 16 * 72; i += 256) sWu[i] = __ldg(wpk_up + i);
+    if (tid < 96) { const int kx = tid & 3; sWo[tid] = kx < 3 ? __ldg(ow.w + (tid >> 2) * 3 + kx) : 0.f; }
+    if (tid == 96) sWo[96] = __ldg(ow.b);
+    float ub[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ub[c] = __ldg(up_b + c);
+    __syncthreads();
+    pdl_wait();                                                    // everything above overlapped the previous kernel's tail
+
+    auto origin = [&](int item, int& b, int& ox0, int& oy0) {
+        b = tg.by_item.div(item);
+        const int t = item - b * (tg.tiles_x * tg.tiles_y);
+        const int tyi = tg.by_x.div(t);
+        ox0 = (t - tyi * tg.tiles_x) * kTailW; oy0 = tyi * TH;
+    };
+    auto issue = [&](int item, int s) {                           // one thread
+        int b, ox0, oy0;
+        origin(item, b, ox0, oy0);
+        const int qy0 = oy0 / 2 - G::LO, qx0 = ox0 / 2 - G::LO;
+        float* dst = sIn + s * G::STAGE;
+        fence_proxy_async();                                       // the stage was last written by generic stores (y in place)
+        mbar_expect_tx(&bars[s], G::STAGE * 4);
+        tma_load_4d(dst, &tmH2, &bars[s], qx0 - G::XH, qy0, 0, b * 16);
+        tma_load_4d(dst + G::H2F, &tmH1, &bars[s], 2 * qx0 - G::XY, 2 * qy0, 0, b * 8);
+    };
+
+    if (tid == 0 && (int)blockIdx.x < tg.ntiles) issue(blockIdx.x, 0);
+    int n = 0;
+    for (int item = blockIdx.x; item < tg.ntiles; item += gridDim.x, ++n) {
+        const int s = n & 1;
+        if (tid == 0 && item + (int)gridDim.x < tg.ntiles) issue(item + gridDim.x, s ^ 1);
+        int b, ox0, oy0;
+        origin(item, b, ox0, oy0);
+        const int qy0 = oy0 / 2 - G::LO, qx0 = ox0 / 2 - G::LO;
+        const float* sH2 = sIn + s * G::STAGE;
+        float* sY = sIn + s * G::STAGE + G::H2F;
+        mbar_wait(&bars[s], (n >> 1) & 1);
+
+        // ---- phase A: one half-resolution quad per thread -> 2x2 pixels x 8 channels of y, in place over h1
+        if (tid < G::QH * G::QW) {
+            const int qy = tid / G::QW, qx = tid - qy * G::QW;
+            const int fy0 = 2 * (qy0 + qy), fx0 = 2 * (qx0 + qx);
+            const bool iny0 = fy0 >= 0 && fy0 < h, iny1 = fy0 + 1 >= 0 && fy0 + 1 < h;      // h, w even: a quad's rows/cols
+            const bool inx = fx0 >= 0 && fx0 < w;                                            // are in or out pairwise
+            float* py = sY + (2 * qy) * G::YP + 2 * qx + G::XY;
+            float acc[4][8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float2 t0 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP);
+                const float2 t1 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP + G::YP);
+                acc[0][c] = ub[c] + t0.x; acc[1][c] = ub[c] + t0.y; acc[2][c] = ub[c] + t1.x; acc[3][c] = ub[c] + t1.y;
+            }
+#pragma unroll 4
+            for (int ci = 0; ci < 16; ++ci) {
+                const float* p = sH2 + (ci * G::HH + qy) * G::HP + qx + G::XH;
+                const float v00 = p[0], v01 = p[1], v10 = p[G::HP], v11 = p[G::HP + 1];
+                const float* wt = sWu + ci * 72;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    acc[0][c] = fmaf(v00, wt[4 * 8 + c], acc[0][c]);
+                    acc[1][c] = fmaf(v00, wt[5 * 8 + c], fmaf(v01, wt[3 * 8 + c], acc[1][c]));
+                    acc[2][c] = fmaf(v00, wt[7 * 8 + c], fmaf(v10, wt[1 * 8 + c], acc[2][c]));
+                    acc[3][c] = fmaf(v00, wt[8 * 8 + c], fmaf(v01, wt[6 * 8 + c], fmaf(v10, wt[2 * 8 + c], fmaf(v11, wt[0 * 8 + c], acc[3][c]))));
+                }
+            }
+            const bool in0 = inx && iny0, in1 = inx && iny1;       // outside the image: the output layer's zero padding
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                *reinterpret_cast<float2*>(py + c * G::YH * G::YP) = in0 ? make_float2(fmaxf(acc[0][c], 0.f), fmaxf(acc[1][c], 0.f)) : make_float2(0.f, 0.f);
+                *reinterpret_cast<float2*>(py + c * G::YH * G::YP + G::YP) = in1 ? make_float2(fmaxf(acc[2][c], 0.f), fmaxf(acc[3][c], 0.f)) : make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B: output layer; lane = column, warp = R consecutive rows
+        const int ty0 = wp * G::R, x = ox0 + lane;
+        const float ob = sWo[96];
+        if (!UP) {
+            float lg[G::R];
+#pragma unroll
+            for (int r = 0; r < G::R; ++r) lg[r] = ob;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                float4 wk[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) wk[ky] = *reinterpret_cast<const float4*>(sWo + (ci * 3 + ky) * 4);
+#pragma unroll
+                for (int rr = 0; rr < G::R + 2; ++rr) {            // y row oy0 + ty0 + rr - 1 = box row ty0 + rr + 1
+                    const float* p = sY + (ci * G::YH + ty0 + rr + 1) * G::YP + lane + 1 + G::XY;
+                    const float v0 = p[0], v1 = p[1], v2 = p[2];
+#pragma unroll
+                    for (int r = 0; r < G::R; ++r) {
+                        const int ky = rr - r;
+                        if (ky >= 0 && ky < 3) lg[r] = fmaf(v0, wk[ky].x, fmaf(v1, wk[ky].y, fmaf(v2, wk[ky].z, lg[r])));
+                    }
+                }
+            }
+            if (x < w) {
+#pragma unroll
+                for (int r = 0; r < G::R; ++r)
+                    if (oy0 + ty0 + r < h) logits[((size_t)b * D + k) * hw + (size_t)(oy0 + ty0 + r) * w + x] = lg[r];
+            }
+        } else {
+            float lg[G::R][4];
+#pragma unroll
+            for (int r = 0; r < G::R; ++r) lg[r][0] = lg[r][1] = lg[r][2] = lg[r][3] = ob;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                float4 wk[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) wk[ky] = *reinterpret_cast<const float4*>(sWo + (ci * 3 + ky) * 4);
+                float va[G::R + 1], vb[G::R + 1];                  // y(row, x), y(row, x + 1); zero beyond the image (phase A)
+#pragma unroll
+                for (int rr = 0; rr < G::R + 1; ++rr) {
+                    const float* p = sY + (ci * G::YH + ty0 + rr) * G::YP + lane;
+                    va[rr] = p[0]; vb[rr] = p[1];
+                }
+#pragma unroll
+                for (int r = 0; r < G::R; ++r) {
+                    const float v00 = va[r], v01 = vb[r], v10 = va[r + 1], v11 = vb[r + 1];
+                    lg[r][0] = fmaf(v00, wk[1].y, lg[r][0]);
+                    lg[r][1] = fmaf(v00, wk[1].z, fmaf(v01, wk[1].x, lg[r][1]));
+                    lg[r][2] = fmaf(v00, wk[2].y, fmaf(v10, wk[0].y, lg[r][2]));
+                    lg[r][3] = fmaf(v00, wk[2].z, fmaf(v01, wk[2].x, fmaf(v10, wk[0].z, fmaf(v11, wk[0].x, lg[r][3]))));
+                }
+            }
+            if (x < w) {
+                const int Wo = 2 * w;
+#pragma unroll
+                for (int r = 0; r < G::R; ++r) {
+                    const int y0 = oy0 + ty0 + r;
+                    if (y0 >= h) break;
+                    float* po = logits + ((size_t)b * D + k) * (4 * hw) + (size_t)(2 * y0) * Wo + 2 * x;
+                    *reinterpret_cast<float2*>(po) = make_float2(lg[r][0], lg[r][1]);
+                    *reinterpret_cast<float2*>(po + Wo) = make_float2(lg[r][2], lg[r][3]);
+                }
+            }
+        }
+        __syncthreads();                                           // y fully consumed before the tile after next lands here
+    }
+}
+
+template <bool UP, int TH>
+static cudaError_t launch_tail_tma(const CUtensorMap& tmH2, const CUtensorMap& tmH1, const float* wpk_up, const float* up_b,
+                                   OutWeights ow, float* logits, int k, int D, int h, int w, int B, cudaStream_t st) {
+    using G = TailTma<UP, TH>;
+    auto kern = tail_tma_kernel<UP, TH>;
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 64 ? dev : 63;
+    if (!ready[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        if (e != cudaSuccess) return e;
+        ready[dev] = true;
+    }
+    TileGrid tg{};
+    tg.tiles_x = (w + kTailW - 1) / kTailW;
+    tg.tiles_y = (h + TH - 1) / TH;
+    tg.ntiles = tg.tiles_x * tg.tiles_y * B;
+    if (tg.ntiles >= (1 << 26)) return cudaErrorInvalidValue;
+    tg.by_x = FastDiv(tg.tiles_x); tg.by_item = FastDiv(tg.tiles_x * tg.tiles_y);
+    int ctas = 2 * sm_count();
+    if (ctas > tg.ntiles) ctas = tg.ntiles;
+    return launch_pdl(kern, dim3(ctas), dim3(256), G::SMEM, st, tmH2, tmH1, wpk_up, up_b, ow, logits, k, D, h, w, tg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Regression over the logit volume, once per stage: one thread per output pixel walks the D planes (every load a
 // coalesced row segment) with the running softmax / un-shifted-exp state in registers.
 // The state used to live in global memory and was updated by the tail of every plane: 24 B read + written per output
@@ -489,6 +699,28 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
         if (!ok) return ADAMVS_EINVAL;
     }
 
+    // tail: TMA-fed persistent kernel when the rows are TMA-addressable; 32x24 tiles when there are enough of them to
+    // keep 2 CTAs per SM busy for several rounds, else 32x16 (ADAMVS_TAIL_CFG=0|16|24: test / measurement hook)
+    int tail_th = 0;
+    CUtensorMap tmH2, tmH1;
+    if (tma) {
+        static const int forced = [] {
+            const char* e = getenv("ADAMVS_TAIL_CFG");
+            return !e ? -1 : !strcmp(e, "0") ? 0 : !strcmp(e, "16") ? 16 : !strcmp(e, "24") ? 24 : -1;
+        }();
+        const long long items24 = (long long)((w + kTailW - 1) / kTailW) * ((h + 23) / 24) * B;
+        tail_th = forced >= 0 ? forced : (items24 >= 8LL * 2 * sm_count() ? 24 : 16);
+        if (!out_up && tail_th == 24) tail_th = 16;             // the stage-3 form's wider boxes: two CTAs per SM only at 32x16
+        if (tail_th) {
+            int hp, hh, yp, yh;
+            auto geom = [&](auto g) { using T = decltype(g); hp = T::HP; hh = T::HH; yp = T::YP; yh = T::YH; };
+            if (out_up) { if (tail_th == 24) geom(TailTma<true, 24>{}); else geom(TailTma<true, 16>{}); }
+            else geom(TailTma<false, 16>{});
+            if (!make_tmap_4d(&tmH2, ws.h2, w2, h2, 1, (long long)B * 16, hp, hh, 16) ||
+                !make_tmap_4d(&tmH1, ws.h1, w, h, 1, (long long)B * 8, yp, yh, 8)) tail_th = 0;
+        }
+    }
+
     for (int k = 0; k < D; ++k) {
         if (tma) {
             if (tc1) {
@@ -518,8 +750,13 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
             ADAMVS_TRY((launch_conv_auto<16, 16, 32, 16, 1, EPI_GATES>(a5, B, st)));
             ADAMVS_TRY((launch_conv_auto<16, 16, 16, 16, 1, EPI_CAND>(a6, B, st)));
         }
-        // 7+8: up1 + skip + relu -> output layer -> online regression, one launch
-        {
+        // 7+8: up1 + skip + relu -> output layer -> logits[:, k], one launch
+        if (tail_th == 24) {
+            ADAMVS_TRY((launch_tail_tma<true, 24>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
+        } else if (tail_th == 16) {
+            if (out_up) ADAMVS_TRY((launch_tail_tma<true, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
+            else ADAMVS_TRY((launch_tail_tma<false, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
+        } else {
             dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
             if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, logits, k, D, h, w));
             else ADAMVS_TRY(launch_pdl(tail_regress_kernel<false>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, logits, k, D, h, w));
