@@ -204,7 +204,8 @@ tail_regress_kernel(const float* h2s, const float* __restrict__ wpk_up, const fl
 template <bool UP, int TH>
 struct TailTma {
     static constexpr int LO = UP ? 0 : 1;
-    static constexpr int QH = TH / 2 + 1 + LO, QW = kTailW / 2 + 1 + LO;          // quads (rows x cols)
+    static constexpr int QH = (TH / 2 + 1 + LO + 1) / 2 * 2, QW = kTailW / 2 + 1 + LO;   // quads (rows, rounded up to pairs, x cols)
+    static constexpr int NPAIR = QH / 2 * QW;                                      // vertical quad pairs; x 2 channel halves = threads
     // TMA boxes start on 16-byte boundaries of the global rows: the quads of the stage-3 form begin one quad left of the
     // tile (x = 16t - 1 at half, 32t - 2 at full resolution), so its boxes begin 3 / 2 columns further left
     static constexpr int XH = UP ? 0 : 3, XY = UP ? 0 : 2;                         // first used column of the h2 / h1 box
@@ -213,7 +214,7 @@ struct TailTma {
     static constexpr int H2F = 16 * HH * HP, H1F = 8 * YH * YP, STAGE = H2F + H1F; // floats; both multiples of 32
     static constexpr int R = TH / 8;                                               // output rows per thread (8 warps)
     static constexpr size_t SMEM = sizeof(float) * (2 * STAGE + 16 * 72 + 8 * 3 * 4 + 4) + 2 * sizeof(uint64_t);
-    static_assert(QH * QW <= 256 && TH % 8 == 0 && XY + 2 * QW <= YP && XH + QW + 1 <= HP, "tile geometry");
+    static_assert(2 * NPAIR <= 256 && TH % 8 == 0 && XY + 2 * QW <= YP && XH + QW + 1 <= HP, "tile geometry");
     static_assert(2 * SMEM + 2048 <= 227 * 1024, "two CTAs per SM");
     static_assert((H2F * 4) % 128 == 0 && (H1F * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
 };
@@ -237,9 +238,13 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant_
     for (int i = tid; i < 16 * 72; i += 256) sWu[i] = __ldg(wpk_up + i);
     if (tid < 96) { const int kx = tid & 3; sWo[tid] = kx < 3 ? __ldg(ow.w + (tid >> 2) * 3 + kx) : 0.f; }
     if (tid == 96) sWo[96] = __ldg(ow.b);
-    float ub[8];
+    // phase-A role of this thread (the same for every tile): quad pair (rows 2*pa_qi, 2*pa_qi + 1; column pa_qx), channels pa_c0 ..+3
+    const bool pa_on = tid < 2 * G::NPAIR;
+    const int pa_half = tid >= G::NPAIR, pa_pr = tid - pa_half * G::NPAIR;
+    const int pa_qi = pa_pr / G::QW, pa_qx = pa_pr - pa_qi * G::QW, pa_c0 = 4 * pa_half;
+    float ub[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) ub[c] = __ldg(up_b + c);
+    for (int c = 0; c < 4; ++c) ub[c] = __ldg(up_b + pa_c0 + c);
     __syncthreads();
     pdl_wait();                                                    // everything above overlapped the previous kernel's tail
 
@@ -272,38 +277,51 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant_
         float* sY = sIn + s * G::STAGE + G::H2F;
         mbar_wait(&bars[s], (n >> 1) & 1);
 
-        // ---- phase A: one half-resolution quad per thread -> 2x2 pixels x 8 channels of y, in place over h1
-        if (tid < G::QH * G::QW) {
-            const int qy = tid / G::QW, qx = tid - qy * G::QW;
-            const int fy0 = 2 * (qy0 + qy), fx0 = 2 * (qx0 + qx);
-            const bool iny0 = fy0 >= 0 && fy0 < h, iny1 = fy0 + 1 >= 0 && fy0 + 1 < h;      // h, w even: a quad's rows/cols
-            const bool inx = fx0 >= 0 && fx0 < w;                                            // are in or out pairwise
-            float* py = sY + (2 * qy) * G::YP + 2 * qx + G::XY;
-            float acc[4][8];
+        // ---- phase A: y in place over h1.  A thread owns two vertically adjacent half-resolution quads (2 x 2x2 pixels)
+        // and four of the eight channels: per input channel 6 input loads + 9 broadcast weight vectors feed 72 FFMA
+        // (one quad x eight channels needed 4 + 18: the kernel was bound by shared-memory wavefronts, l1tex 86 %)
+        if (pa_on) {
+            const int fx0 = 2 * (qx0 + pa_qx);
+            const bool inx = fx0 >= 0 && fx0 < w;                  // h, w even: a quad's rows / columns are in or out pairwise
+            float* py = sY + (4 * pa_qi) * G::YP + 2 * pa_qx + G::XY + pa_c0 * G::YH * G::YP;
+            float acc[2][4][4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float2 t0 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP);
-                const float2 t1 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP + G::YP);
-                acc[0][c] = ub[c] + t0.x; acc[1][c] = ub[c] + t0.y; acc[2][c] = ub[c] + t1.x; acc[3][c] = ub[c] + t1.y;
-            }
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 t0 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP + (2 * q) * G::YP);
+                    const float2 t1 = *reinterpret_cast<const float2*>(py + c * G::YH * G::YP + (2 * q + 1) * G::YP);
+                    acc[q][0][c] = ub[c] + t0.x; acc[q][1][c] = ub[c] + t0.y; acc[q][2][c] = ub[c] + t1.x; acc[q][3][c] = ub[c] + t1.y;
+                }
 #pragma unroll 4
             for (int ci = 0; ci < 16; ++ci) {
-                const float* p = sH2 + (ci * G::HH + qy) * G::HP + qx + G::XH;
-                const float v00 = p[0], v01 = p[1], v10 = p[G::HP], v11 = p[G::HP + 1];
-                const float* wt = sWu + ci * 72;
+                const float* p = sH2 + (ci * G::HH + 2 * pa_qi) * G::HP + pa_qx + G::XH;
+                float v[3][2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    acc[0][c] = fmaf(v00, wt[4 * 8 + c], acc[0][c]);
-                    acc[1][c] = fmaf(v00, wt[5 * 8 + c], fmaf(v01, wt[3 * 8 + c], acc[1][c]));
-                    acc[2][c] = fmaf(v00, wt[7 * 8 + c], fmaf(v10, wt[1 * 8 + c], acc[2][c]));
-                    acc[3][c] = fmaf(v00, wt[8 * 8 + c], fmaf(v01, wt[6 * 8 + c], fmaf(v10, wt[2 * 8 + c], fmaf(v11, wt[0 * 8 + c], acc[3][c]))));
-                }
+                for (int r = 0; r < 3; ++r) { v[r][0] = p[r * G::HP]; v[r][1] = p[r * G::HP + 1]; }
+                const float* wt = sWu + ci * 72 + pa_c0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float v00 = v[q][0], v01 = v[q][1], v10 = v[q + 1][0], v11 = v[q + 1][1];
+                        acc[q][0][c] = fmaf(v00, wt[4 * 8 + c], acc[q][0][c]);
+                        acc[q][1][c] = fmaf(v00, wt[5 * 8 + c], fmaf(v01, wt[3 * 8 + c], acc[q][1][c]));
+                        acc[q][2][c] = fmaf(v00, wt[7 * 8 + c], fmaf(v10, wt[1 * 8 + c], acc[q][2][c]));
+                        acc[q][3][c] = fmaf(v00, wt[8 * 8 + c], fmaf(v01, wt[6 * 8 + c], fmaf(v10, wt[2 * 8 + c], fmaf(v11, wt[0 * 8 + c], acc[q][3][c]))));
+                    }
             }
-            const bool in0 = inx && iny0, in1 = inx && iny1;       // outside the image: the output layer's zero padding
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                *reinterpret_cast<float2*>(py + c * G::YH * G::YP) = in0 ? make_float2(fmaxf(acc[0][c], 0.f), fmaxf(acc[1][c], 0.f)) : make_float2(0.f, 0.f);
-                *reinterpret_cast<float2*>(py + c * G::YH * G::YP + G::YP) = in1 ? make_float2(fmaxf(acc[2][c], 0.f), fmaxf(acc[3][c], 0.f)) : make_float2(0.f, 0.f);
+            for (int q = 0; q < 2; ++q) {
+                const int fy0 = 2 * (qy0 + 2 * pa_qi + q);
+                const bool in0 = inx && fy0 >= 0 && fy0 < h, in1 = inx && fy0 + 1 >= 0 && fy0 + 1 < h;   // outside the image: the output layer's zero padding
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<float2*>(py + c * G::YH * G::YP + (2 * q) * G::YP) =
+                        in0 ? make_float2(fmaxf(acc[q][0][c], 0.f), fmaxf(acc[q][1][c], 0.f)) : make_float2(0.f, 0.f);
+                    *reinterpret_cast<float2*>(py + c * G::YH * G::YP + (2 * q + 1) * G::YP) =
+                        in1 ? make_float2(fmaxf(acc[q][2][c], 0.f), fmaxf(acc[q][3][c], 0.f)) : make_float2(0.f, 0.f);
+                }
             }
         }
         __syncthreads();
