@@ -1,5 +1,5 @@
 // 3x3 stride-1 convolutions of the recurrent regulariser on the 5th-generation tensor cores: tcgen05.mma kind::tf32,
-// accumulators in TMEM, at fp32 accuracy through an exact hi/lo operand split ("3xTF32", here all four partial products).
+// accumulators in TMEM, at fp32 accuracy through a hi/lo operand split ("3xTF32": the three partial products that matter).
 //
 // Implicit GEMM without an im2col copy.  A tile's input (4*MT + 2 rows x 32 columns, halo included) sits in shared
 // memory as [8-channel chunk][hi|lo][channel quad][position][4 channels], positions row-major with pitch 32, 16 bytes per
@@ -17,10 +17,13 @@
 // (6 per 128 positions and chunk: 49 clk each at N = 48 / 96, 96 clk at N = 192).
 //
 // fp32 accuracy: kind::tf32 reads the top 19 bits of each fp32 word.  Activations and weights are split into
-// hi = rna_tf32(x), lo = rna_tf32(x - hi) (|x - hi - lo| <= 2^-23 |x|); the B operand carries [W_hi rows | W_lo rows]
-// per kx, A_hi and A_lo are multiplied with it in turn and the epilogue adds the two column halves:
-// (A_hi + A_lo)(W_hi + W_lo), fp32 accumulation in TMEM.  PREC_TF32 drops the A_lo pass (activations rounded to tf32,
-// weights still exact): half the MMAs, reported separately with its own tolerance.
+// hi = rna_tf32(x), lo = rna_tf32(x - hi) (|x - hi - lo| <= 2^-23 |x|); the B operand carries [W_hi rows of the three
+// kx | W_lo rows of the three kx]; A_hi is multiplied with all of it, A_lo with the W_hi rows only (a smaller N on the
+// same operand) and the epilogue adds the two column halves: A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation in
+// TMEM.  The dropped A_lo W_lo term is <= 2^-22 |a||w| per product, below the rounding of the fp32 accumulation itself
+// (round 2: it had been computed too - all four products; dropping it shortens the second pass from N = 6 Cout to
+// 3 Cout: 11-15 % less tensor-pipe time and operand traffic).  PREC_TF32 drops the A_lo pass altogether (activations
+// rounded to tf32, weights still exact), reported separately with its own tolerance.
 //
 // Warp-specialised persistent CTA (one per SM, 512 threads), static round-robin tile schedule:
 //   warp 8 lane 0   TMA producer: planar [8 ch][4*MT+2][36] boxes (out-of-image elements zero-filled = conv padding)
@@ -131,7 +134,8 @@ struct TcCfg {
     using G = TcGeom<MT>;
     static constexpr int CIN = CA + CB, NCH = CIN / CK;           // 8-channel chunks = K steps per tap row
     static constexpr int NB = 2 * COUT;                            // [W_hi rows | W_lo rows] of one kx
-    static constexpr int N3 = 3 * NB;                              // MMA N: kx-major
+    static constexpr int N3 = 3 * NB;                              // MMA N: [W_hi: kx0 kx1 kx2 | W_lo: kx0 kx1 kx2] x COUT rows
+    static constexpr int NLO = (3 * COUT + 15) / 16 * 16;          // N of the A_lo pass: the W_hi rows
     static constexpr int NHL = PREC == PREC_FP32X3 ? 2 : 1;        // operand passes per stage (hi, lo)
     static constexpr int PLANE_BYTES = G::NPOS * 16;               // one channel quad of one pass
     static constexpr int STAGE_BYTES = NHL * 2 * PLANE_BYTES;      // [hi|lo][2 quads][NPOS][4]
@@ -223,9 +227,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float v = __ldg(a.wpk + ((size_t)(8 * s + 4 * kq + j) * 9 + ky * 3 + kx) * wrow + a.co_off + n);
         float hi, lo;
         split_tf32(v, hi, lo);
-        float* dst = reinterpret_cast<float*>(sB + (size_t)(ky * C::NCH + s) * C::B_STEP_BYTES + kq * C::N3 * 16) + kx * C::NB * 4;
-        dst[n * 4 + j] = hi;
-        dst[(COUT + n) * 4 + j] = lo;
+        float* dst = reinterpret_cast<float*>(sB + (size_t)(ky * C::NCH + s) * C::B_STEP_BYTES + kq * C::N3 * 16);
+        dst[(kx * COUT + n) * 4 + j] = hi;
+        dst[((3 + kx) * COUT + n) * 4 + j] = lo;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -270,7 +274,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 9) {
         // ===== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(C::N3);
+            // A_hi meets all of [W_hi | W_lo]; A_lo only the W_hi rows (rounded up to the MMA's N granularity: with 8 or 24
+            // output channels that includes eight W_lo rows, a harmless part of the dropped lo x lo term)
+            const uint32_t idesc_hl[2] = {umma_idesc_tf32(C::N3), umma_idesc_tf32(C::NLO)};
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             int g = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
@@ -296,7 +302,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             for (int mt = 0; mt < MT; ++mt) {
                                 const uint32_t d = tmem + (uint32_t)(acc * C::ACC_COLS + mt * C::N3);
                                 const uint64_t ad = ad00 + (uint64_t)((hl * 2 * C::PLANE_BYTES + (mt * 128 + ky * G::PW) * 16) >> 4);
-                                umma_tf32(d, ad, bd, idesc, (ky | hl) ? 1u : (c ? 1u : 0u));
+                                umma_tf32(d, ad, bd, idesc_hl[hl], (ky | hl) ? 1u : (c ? 1u : 0u));
                             }
                         }
                     }
@@ -386,8 +392,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint32_t rh[3][8], rl[3][8];
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    tmem_ld8_issue(taddr + kx * C::NB + c0, rh[kx]);
-                    tmem_ld8_issue(taddr + kx * C::NB + COUT + c0, rl[kx]);
+                    tmem_ld8_issue(taddr + kx * COUT + c0, rh[kx]);
+                    tmem_ld8_issue(taddr + (3 + kx) * COUT + c0, rl[kx]);
                 }
                 tmem_ld_wait();
                 if (tid == 0 && gi == 0) TC_TRACE(3, ti, 0);

@@ -495,12 +495,13 @@ def main():
             if msred:
                 entry["bound"] = "fp32 FFMA (GroupNorm conv-GRU on the FFMA kernels)"
             else:
-                # fp32 accuracy on kind::tf32: (A_hi + A_lo)(W_hi + W_lo) = 4 tf32 products per fp32 product;
+                # fp32 accuracy on kind::tf32: A_hi W_hi + A_hi W_lo + A_lo W_hi = 3 tf32 products per fp32 product
+                # (the 8-channel layers' second pass is padded from N = 24 to 32, not counted);
                 # --math tf32 drops the A_lo pass: 2 per product
-                passes = 2 if args.math == "tf32" else 4
+                passes = 2 if args.math == "tf32" else 3
                 tcf = regnet_tc_flops(B, C, D, h, w)
                 entry.update({"bound": "tensor (tcgen05 kind::tf32" + (", single-pass activations" if args.math == "tf32" else
-                                                                        ", exact hi/lo operand split") + "; conv2 + tail on FFMA)",
+                                                                        ", hi/lo operand split, 3 products") + "; conv2 + tail on FFMA)",
                               "tensor_share_of_flops": tcf / fl,
                               "tf32_TFLOPs_issued": passes * tcf / st["ms_mean"] * 1e-9,
                               "tf32_issue_utilisation": passes * tcf / st["ms_mean"] * 1e-9 / tf32_peak,
