@@ -247,8 +247,152 @@ deconv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wpk, co
     }
 }
 
+// The same transposed convolution, TMA-fed and persistent (win % 4 == 0).  The kernel above re-reads its input from
+// global memory for every block of 8 output channels, with nothing in flight while it computes (20-23 TFLOP/s).  Here a
+// CTA owns one block of 8 output channels (its weights resident in shared memory) and walks over tiles of 32 x 8 input
+// pixels; the input arrives as [8 channels][9 rows][36 columns] boxes (right / bottom neighbours included, image borders
+// zero-filled) through a ring that stays three boxes ahead.  A thread owns two vertically adjacent input pixels (2 x 2x2
+// outputs) and four channels: per input channel 6 input loads + 9 broadcast weight vectors feed 72 FFMA (the K3 tail's
+// mapping, regnet.cu).  Same FFMA order per output as above: bit-identical results.
+constexpr int kDcW = 32, kDcH = 8, kDcBoxW = 36, kDcBoxH = kDcH + 1, kDcStages = 4;
+constexpr int kDcStageFloats = 8 * kDcBoxH * kDcBoxW;
+
+template <int CIN>
+constexpr size_t deconv_tma_smem() { return sizeof(float) * (kDcStages * kDcStageFloats + CIN * 72) + kDcStages * sizeof(uint64_t); }
+
+template <int CIN, int COUT>
+static __global__ void __launch_bounds__(256, 2)
+deconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ bias, int relu,
+                     const float* __restrict__ residual, float* __restrict__ out, int hin, int win, TileGrid tg) {
+    constexpr int NCH = CIN / 8;
+    static_assert((kDcStageFloats * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sIn = reinterpret_cast<float*>(smem_raw);                       // [kDcStages][8][9][36]
+    float* sW = sIn + kDcStages * kDcStageFloats;                          // [CIN][9][8] of this CTA's channel block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + CIN * 72);
+    const int tid = threadIdx.x, cob = blockIdx.y;
+    if (tid == 0) { for (int i = 0; i < kDcStages; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    for (int i = tid; i < CIN * 72; i += 256) sW[i] = __ldg(wpk + (size_t)(i / 8) * COUT + cob * 8 + (i % 8));
+    // this thread: input rows 2*qi, 2*qi + 1 of the tile, column j, output channels cob*8 + c0 .. + 3
+    const int half = tid >> 7, pr = tid & 127, qi = pr >> 5, j = pr & 31, c0 = 4 * half;
+    float bc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bc[c] = __ldg(bias + cob * 8 + c0 + c);
+    __syncthreads();
+
+    const int my_tiles = (tg.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * NCH;                                      // chunk stream of this CTA
+    const int tiles_per_item = tg.tiles_x * tg.tiles_y;
+    auto tile_origin = [&](int ti, int& b, int& ix0, int& iy0) {
+        const int tile = blockIdx.x + ti * gridDim.x;
+        b = tg.by_item.div(tile);
+        const int r = tile - b * tiles_per_item, ty = tg.by_x.div(r);
+        ix0 = (r - ty * tg.tiles_x) * kDcW; iy0 = ty * kDcH;
+    };
+    auto issue = [&](int g) {                                              // one thread
+        const int ti = g / NCH, c = g - ti * NCH, s = g % kDcStages;
+        int b, ix0, iy0;
+        tile_origin(ti, b, ix0, iy0);
+        fence_proxy_async();
+        mbar_expect_tx(&bars[s], kDcStageFloats * 4);
+        tma_load_4d(sIn + s * kDcStageFloats, &tmIn, &bars[s], ix0, iy0, 0, b * CIN + c * 8);
+    };
+    if (tid == 0)
+        for (int g = 0; g < kDcStages - 1 && g < total; ++g) issue(g);
+
+    const size_t ip = (size_t)hin * win;
+    const int wout = 2 * win;
+    int g = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        int b, ix0, iy0;
+        tile_origin(ti, b, ix0, iy0);
+        float acc[2][4][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[q][k][c] = 0.f;
+        for (int ch = 0; ch < NCH; ++ch, ++g) {
+            const int s = g % kDcStages;
+            if (tid == 0 && g + kDcStages - 1 < total) issue(g + kDcStages - 1);   // its slot was consumed in iteration g - 1
+            mbar_wait(&bars[s], (g / kDcStages) & 1);
+            const float* st = sIn + s * kDcStageFloats + (2 * qi) * kDcBoxW + j;
+#pragma unroll 4
+            for (int cc = 0; cc < 8; ++cc) {
+                const float* p = st + cc * kDcBoxH * kDcBoxW;
+                float v[3][2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { v[r][0] = p[r * kDcBoxW]; v[r][1] = p[r * kDcBoxW + 1]; }
+                const float* w = sW + (ch * 8 + cc) * 72 + c0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float v00 = v[q][0], v01 = v[q][1], v10 = v[q + 1][0], v11 = v[q + 1][1];
+                        acc[q][0][c] = fmaf(v00, w[4 * 8 + c], acc[q][0][c]);
+                        acc[q][1][c] = fmaf(v01, w[3 * 8 + c], fmaf(v00, w[5 * 8 + c], acc[q][1][c]));
+                        acc[q][2][c] = fmaf(v10, w[1 * 8 + c], fmaf(v00, w[7 * 8 + c], acc[q][2][c]));
+                        acc[q][3][c] = fmaf(v11, w[0 * 8 + c], fmaf(v10, w[2 * 8 + c], fmaf(v01, w[6 * 8 + c], fmaf(v00, w[8 * 8 + c], acc[q][3][c]))));
+                    }
+            }
+            __syncthreads();                                               // stage s consumed: the next issue may refill it
+        }
+        const int ix = ix0 + j;
+        if (ix < win) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int iy = iy0 + 2 * qi + q;
+                if (iy >= hin) break;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float r[4] = {acc[q][0][c] + bc[c], acc[q][1][c] + bc[c], acc[q][2][c] + bc[c], acc[q][3][c] + bc[c]};
+                    if (relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+                    const size_t o = ((size_t)b * COUT + cob * 8 + c0 + c) * 4 * ip + (size_t)(2 * iy) * wout + 2 * ix;
+                    if (residual) {                      // skip connection added after the activation (adamvs.py:233-235)
+                        const float2 s0 = *reinterpret_cast<const float2*>(residual + o), s1 = *reinterpret_cast<const float2*>(residual + o + wout);
+                        r[0] += s0.x; r[1] += s0.y; r[2] += s1.x; r[3] += s1.y;
+                    }
+                    *reinterpret_cast<float2*>(out + o) = make_float2(r[0], r[1]);
+                    *reinterpret_cast<float2*>(out + o + wout) = make_float2(r[2], r[3]);
+                }
+            }
+        }
+    }
+}
+
 template <int CIN, int COUT>
 static int launch_deconv(const float* in, const float* wpk, const float* bias, int relu, const float* residual, float* out, int N, int hin, int win, cudaStream_t st) {
+    // ADAMVS_DECONV_CFG=0 keeps the plain kernel (test / measurement hook, read once per process)
+    static const bool tma_allowed = [] { const char* e = getenv("ADAMVS_DECONV_CFG"); return !(e && *e == '0'); }();
+    if (tma_allowed && win % 4 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && hin < 65535 && win < 65535) {
+        CUtensorMap tm;
+        TileGrid tg{};
+        tg.tiles_x = (win + kDcW - 1) / kDcW;
+        tg.tiles_y = (hin + kDcH - 1) / kDcH;
+        const long long nt = (long long)tg.tiles_x * tg.tiles_y * N;
+        if (nt < (1 << 26) && make_tmap_4d(&tm, in, win, hin, 1, (long long)N * CIN, kDcBoxW, kDcBoxH, 8)) {
+            tg.ntiles = (int)nt;
+            tg.by_x = FastDiv(tg.tiles_x); tg.by_item = FastDiv(tg.tiles_x * tg.tiles_y);
+            auto kern = deconv3x3_tma_kernel<CIN, COUT>;
+            constexpr size_t smem = deconv_tma_smem<CIN>();
+            static bool ready[64] = {false};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev = dev < 64 ? dev : 63;
+            if (!ready[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                ready[dev] = true;
+            }
+            constexpr int ncob = COUT / 8;
+            int ctas = 2 * sm_count() / ncob;                // two CTAs per SM over all channel blocks
+            if (ctas < 1) ctas = 1;
+            if (ctas > tg.ntiles) ctas = tg.ntiles;
+            kern<<<dim3(ctas, ncob), 256, smem, st>>>(tm, wpk, bias, relu, residual, out, hin, win, tg);
+            ADAMVS_LAUNCH_RESULT();
+        }
+    }
     if ((long long)hin * (COUT / 8) > 65535 || N > 65535) return ADAMVS_EINVAL;
     dim3 grid((win + 127) / 128, hin * (COUT / 8), N);
     deconv3x3_kernel<CIN, COUT><<<grid, 128, 0, st>>>(in, wpk, bias, relu, residual, out, hin, win);

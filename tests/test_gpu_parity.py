@@ -694,15 +694,25 @@ def test_context_head_vs_torch(cx, cctx, cout, h, w):
     assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
 
 
-@pytest.mark.parametrize("cin,cout,h,w", [(32, 16, 12, 20), (16, 8, 24, 36), (48, 48, 6, 10)])
+@pytest.mark.parametrize("cin,cout,h,w", [(32, 16, 12, 20), (16, 8, 24, 36), (48, 48, 6, 10),       # w % 4 != 0: the plain kernel
+                                          (16, 8, 21, 72), (32, 16, 9, 100), (48, 48, 18, 40)])     # several tiles, ragged edges
 def test_native_deconv3x3_vs_torch(cin, cout, h, w):
+    """Transposed 3x3 stride-2 convolution (+ bias, ReLU, optional skip addition after the activation): the TMA-fed
+    persistent kernel (w % 4 == 0) and the plain one against torch."""
     ops = _ops()
     g = torch.Generator().manual_seed(cin + h)
-    x = torch.randn(2, cin, h, w, generator=g)
+    x = torch.randn(3, cin, h, w, generator=g)
     wt = torch.randn(cin, cout, 3, 3, generator=g) / (3.0 * cin ** 0.5)
     bias = torch.randn(cout, generator=g)
+    skip = torch.randn(3, cout, 2 * h, 2 * w, generator=g)
     want = F.relu(F.conv_transpose2d(x, wt, bias, stride=2, padding=1, output_padding=1))
-    got = ops.deconv3x3(x.to(_dev()), ops.pack_deconv3x3_weight(wt).to(_dev()), bias.to(_dev()), True).cpu()
+    wpk = ops.pack_deconv3x3_weight(wt).to(_dev())
+    got = ops.deconv3x3(x.to(_dev()), wpk, bias.to(_dev()), True).cpu()
+    assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
+    got = ops.deconv3x3(x.to(_dev()), wpk, bias.to(_dev()), True, skip.to(_dev())).cpu()
+    assert abs_err(got, want + skip) < 2e-5 * max(1.0, float((want + skip).abs().max()))
+    want = F.conv_transpose2d(x, wt, bias, stride=2, padding=1, output_padding=1)
+    got = ops.deconv3x3(x.to(_dev()), wpk, bias.to(_dev()), False).cpu()
     assert abs_err(got, want) < 2e-5 * max(1.0, float(want.abs().max()))
 
 
