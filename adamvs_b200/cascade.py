@@ -21,10 +21,13 @@ _STAGES = ("stage1", "stage2", "stage3")
 
 
 def _true_fp32():
-    # The few layers still on torch (average pools + 1x1 convs of the pooled context maps; everything under train())
-    # must not run in cuDNN's default TF32, which alone breaks the 1e-4 probability tolerance.
+    # Layers that fall back to torch (channel counts the native kernels do not cover, e.g. the pair U-Net's stride-2 and
+    # transposed convolutions when ndepths[0] != 48; everything under train()) must not run in cuDNN's default TF32, which
+    # alone breaks the 1e-4 probability tolerance - and must be deterministic: cuDNN's default choice for
+    # the transposed convolutions uses atomics, which made the stage-1 pair logits (and now and then a depth value in the
+    # last bit) differ from run to run at ndepths[0] = 8 (tools/gpu_r2z2.sh; the all-native 48-plane path never did).
     return torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                      deterministic=False, allow_tf32=False)
+                                      deterministic=True, allow_tf32=False)
 
 
 def extract_features(net, imgs: torch.Tensor) -> Dict[str, torch.Tensor]:

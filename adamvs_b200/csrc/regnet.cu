@@ -323,6 +323,10 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant_
                         in1 ? make_float2(fmaxf(acc[q][2][c], 0.f), fmaxf(acc[q][3][c], 0.f)) : make_float2(0.f, 0.f);
                 }
             }
+            // these generic-proxy stores share their buffer with the TMA write of the tile after next: order them against
+            // the async proxy here, in the writing thread (a fence in the issuing thread alone left a rare run-to-run
+            // difference in test_forward_is_bit_reproducible)
+            fence_proxy_async();
         }
         __syncthreads();
 
