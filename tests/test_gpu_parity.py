@@ -267,7 +267,7 @@ def test_forward_matches_reference_golden(name, cls):
 
 @pytest.mark.parametrize("name,cls", [("full_d48", "stream"), ("batch2_d8", "whole")])
 def test_forward_is_bit_reproducible(name, cls):
-    """Three forwards of the same inputs give bit-identical outputs.  The kernels of the recurrent sweep overlap through
+    """Six forwards of the same inputs give bit-identical outputs.  The kernels of the recurrent sweep overlap through
     programmatic dependent launch; a load of the GRU state through the non-coherent L1 path (stale line from the previous
     plane) once made planes >= 1 differ from run to run while staying inside the parity tolerance most of the time."""
     g = load_golden(name)
@@ -276,12 +276,16 @@ def test_forward_is_bit_reproducible(name, cls):
     dv = dv3 if cls == "whole" else dv2
     args = (imgs.to(_dev()), _to_dev(proj), dv.to(_dev()))
     outs = []
-    for _ in range(3):
+    for _ in range(6):
         out = m(*args)
-        outs.append({s: (out[s]["depth"].clone(), out[s]["photometric_confidence"].clone()) for s in ("stage1", "stage2", "stage3")})
+        outs.append({s: (out[s]["depth"].clone(), out[s]["photometric_confidence"].clone(),
+                         torch.stack(out["stage1"]["pair_result"], 1).clone(), torch.stack(out[s]["pair_confidence"][:4], 1).clone())
+                     for s in ("stage1", "stage2", "stage3")})
     for o in outs[1:]:
         for s in ("stage1", "stage2", "stage3"):
-            assert torch.equal(o[s][0], outs[0][s][0]) and torch.equal(o[s][1], outs[0][s][1]), s
+            # the pair maps too: cuDNN's default (atomics) transposed convolutions in the torch-fallback layers of the
+            # 8-plane pair U-Net once differed from run to run in them (cascade._true_fp32 now asks for deterministic ones)
+            assert all(torch.equal(a, b) for a, b in zip(o[s], outs[0][s])), s
 
 
 def test_intermediates_match_reference_golden():
