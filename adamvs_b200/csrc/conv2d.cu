@@ -98,18 +98,50 @@ context_head_kernel(const float* __restrict__ x, const float* __restrict__ a, co
         const int hs = m == 0 ? ha : hc, ws = m == 0 ? wa : wc;
         const Lerp ly = lerp_index(y, (float)hs / (float)h, hs);
         const float* base = src + (size_t)n * CCTX * hs * ws;
+        Lerp lx[PX];
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            const Lerp lx = lerp_index(x0 + p, (float)ws / (float)w, ws);
+        for (int p = 0; p < PX; ++p) lx[p] = lerp_index(x0 + p, (float)ws / (float)w, ws);
+        const int cmin = lx[0].i0;
+        if (lx[PX - 1].i1 - cmin <= 2) {
+            // the PX pixels of a thread sample at most three source columns (maps at 1/4 and 1/8 of x's width: always):
+            // load those once per channel and row - 6 gathers instead of 4 * PX - and give every pixel three column
+            // weights (its two lerp weights on its two columns, zero on the third)
+            float wcol[PX][3];
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    wcol[p][d] = (lx[p].i0 - cmin == d ? lx[p].l0 : 0.f) + (lx[p].i1 - cmin == d ? lx[p].l1 : 0.f);
+            const int c1 = min(cmin + 1, ws - 1), c2 = min(cmin + 2, ws - 1);
 #pragma unroll
             for (int j = 0; j < CCTX; ++j) {
-                const float* pl = base + (size_t)j * hs * ws;
-                const float v00 = __ldg(pl + ly.i0 * ws + lx.i0), v01 = __ldg(pl + ly.i0 * ws + lx.i1);
-                const float v10 = __ldg(pl + ly.i1 * ws + lx.i0), v11 = __ldg(pl + ly.i1 * ws + lx.i1);
-                const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+                const float* r0 = base + (size_t)j * hs * ws + ly.i0 * ws;
+                const float* r1 = base + (size_t)j * hs * ws + ly.i1 * ws;
+                const float a0 = __ldg(r0 + cmin), a1 = __ldg(r0 + c1), a2 = __ldg(r0 + c2);
+                const float b0 = __ldg(r1 + cmin), b1 = __ldg(r1 + c1), b2 = __ldg(r1 + c2);
                 const float* wr = sW + (m * CCTX + j) * COUT;
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[p][co] = fmaf(v, wr[co], acc[p][co]);
+                for (int p = 0; p < PX; ++p) {
+                    const float t0 = fmaf(wcol[p][2], a2, fmaf(wcol[p][1], a1, wcol[p][0] * a0));
+                    const float t1 = fmaf(wcol[p][2], b2, fmaf(wcol[p][1], b1, wcol[p][0] * b0));
+                    const float v = ly.l0 * t0 + ly.l1 * t1;
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[p][co] = fmaf(v, wr[co], acc[p][co]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+#pragma unroll
+                for (int j = 0; j < CCTX; ++j) {
+                    const float* pl = base + (size_t)j * hs * ws;
+                    const float v00 = __ldg(pl + ly.i0 * ws + lx[p].i0), v01 = __ldg(pl + ly.i0 * ws + lx[p].i1);
+                    const float v10 = __ldg(pl + ly.i1 * ws + lx[p].i0), v11 = __ldg(pl + ly.i1 * ws + lx[p].i1);
+                    const float v = ly.l0 * (lx[p].l0 * v00 + lx[p].l1 * v01) + ly.l1 * (lx[p].l0 * v10 + lx[p].l1 * v11);
+                    const float* wr = sW + (m * CCTX + j) * COUT;
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[p][co] = fmaf(v, wr[co], acc[p][co]);
+                }
             }
         }
     }

@@ -115,8 +115,8 @@ int adamvs_regnet_red_f32(const float* volume, const adamvs_regnet_weights* host
 
 /* Arithmetic of the regulariser's 3x3 convolutions.
  *   FFMA     fp32 FFMA direct convolutions.
- *   TC_FP32  tcgen05.mma kind::tf32 with exact hi/lo operand splits (all four partial products, fp32 accumulation in
- *            TMEM): fp32 accuracy, same tolerance as FFMA.
+ *   TC_FP32  tcgen05.mma kind::tf32 with hi/lo operand splits (A_hi W_hi + A_hi W_lo + A_lo W_hi; the dropped A_lo W_lo
+ *            is below the rounding of the fp32 accumulation in TMEM): fp32 accuracy, same tolerance as FFMA.
  *   TC_TF32  activations rounded to tf32 (one pass), weights still split: reported separately with its own tolerance.
  *   AUTO     per layer, whichever of FFMA / TC_FP32 is faster for the plane size (measured on B200):
  *            both are fp32-accurate, so the choice does not change the tolerance.
