@@ -176,7 +176,9 @@ def test_fused_volume_zero_padding_and_behind_camera():
 
 
 @pytest.mark.parametrize("C,D,h,w,up,prob", [(32, 6, 16, 24, True, "softmax"), (16, 4, 32, 48, True, "exp"),
-                                             (8, 3, 64, 96, False, "softmax"), (8, 2, 34, 46, False, "exp")])
+                                             (8, 3, 64, 96, False, "softmax"), (8, 2, 34, 46, False, "exp"),
+                                             # ragged tiles of the TMA-fed tail (w % 8 == 0, neither a multiple of 32 nor of the tile height)
+                                             (16, 3, 38, 72, True, "softmax"), (8, 2, 50, 104, False, "exp")])
 def test_regnet_red_vs_oracle(C, D, h, w, up, prob, math=None):
     """K3 with the regression folded in: logits, depth and confidence against the oracle's plane loop."""
     ops = _ops()
@@ -592,6 +594,23 @@ def test_conv_tile_configurations_forced(cfg):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
                         "test_regnet_red_vs_oracle or test_regnet_msred_vs_oracle or test_forward_matches_reference_golden"],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("var,cfg", [("ADAMVS_TAIL_CFG", "0"), ("ADAMVS_TAIL_CFG", "16"), ("ADAMVS_TAIL_CFG", "24"), ("ADAMVS_DECONV_CFG", "0")])
+def test_tail_and_transposed_conv_variants_forced(var, cfg):
+    """The regulariser's tail picks the plain kernel (rows TMA cannot address), or the TMA-fed one with 32x16 or 32x24
+    tiles (the latter only for thousands of tiles); the transposed convolutions pick the plain or the TMA-fed kernel
+    from the row width.  Each variant is forced in a fresh process and the kernel tests and a whole forward re-run."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, **{var: cfg})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_regnet_red_vs_oracle or test_native_deconv3x3_vs_torch or test_forward_matches_reference_golden or "
+                        "test_feature_net_and_pair_unet_native_vs_oracle"],
                        cwd=root, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
