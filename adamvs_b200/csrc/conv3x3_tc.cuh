@@ -27,8 +27,9 @@
 //
 // Warp-specialised persistent CTA (one per SM, 512 threads), static round-robin tile schedule:
 //   warp 8 lane 0   TMA producer: planar [8 ch][4*MT+2][36] boxes (out-of-image elements zero-filled = conv padding)
-//                   into a ring deep enough to cover the DRAM latency; once per tile also the GRU epilogue operands
-//                   (state h for the reset gates, update gate u and h for the candidate blend) of the OUTPUT tile
+//                   into a ring deep enough to cover the DRAM latency
+//   warp 10 lane 0  TMA producer of the GRU epilogue operands (state h for the reset gates, update gate u and h for the
+//                   candidate blend) of the OUTPUT tile, into their own ring (released by the epilogue)
 //   warps 4-7       converters: planar slot -> split -> hi/lo quad-interleaved operand stage (4 conflict-free LDS.32,
 //                   2 + 2 STS.128 per position; a warp = one row of 32 positions)
 //   warp 9 lane 0   MMA issuer: per chunk 3 (ky) x {hi,lo} x MT MMAs; tcgen05.commit hands the operand stage back to
@@ -142,7 +143,10 @@ struct TcCfg {
     static constexpr int B_STEP_BYTES = 2 * N3 * 16;               // [2 quads][N3 rows][4] of one (ky, chunk)
     static constexpr int B_BYTES = 3 * NCH * B_STEP_BYTES;
     static constexpr int SLOT_BYTES = G::BOX_FLOATS * 4;
-    static constexpr int NA = 3;                                   // operand stages
+    // operand stages: four where at least four TMA slots still fit beside them (the converters waited ~200 clk per chunk
+    // for a free stage with three), else three
+    static constexpr int EPI_TILE_BYTES0 = (EPI == EPI_GATES ? COUT / 2 : (EPI == EPI_CAND ? 2 * COUT : 0)) * G::TH * 32 * 4;
+    static constexpr int NA = (227 * 1024 - 1024 - B_BYTES - 4 * STAGE_BYTES - 3 * EPI_TILE_BYTES0) / SLOT_BYTES >= 4 ? 4 : 3;
     // GRU epilogue operands (h for the reset gates; u and h for the candidate blend) travel like the input: the producer
     // streams [channels][4*MT rows][32] boxes of the output tile into a ring EPI_R tiles deep
     static constexpr int NG_STEPS = MT * (COUT / 8);               // (M tile, 8-channel group) epilogue steps per tile
@@ -170,7 +174,7 @@ struct TcCfg {
 };
 
 // warps 0-3 and 12.. : epilogue, NSET sets of four warps (TMEM lane quarter = warp % 4; set s takes steps s, s + NSET, ..),
-// 4-7 converters, 8 TMA producer, 9 MMA issuer, 10-11 idle.  An epilogue step is a latency chain (TMEM load -> shuffles ->
+// 4-7 converters, 8 input TMA producer, 9 MMA issuer, 10 epilogue-operand TMA producer, 11 idle.  An epilogue step is a latency chain (TMEM load -> shuffles ->
 // MUFU -> stores, ~1 kclk for ~150 instructions).  MEASURED (round 2, bench B = 32, profiles/r2d_k3_epilogue_sets.txt):
 // NSET = 2 / 3 / 4 (512 / 640 / 768 threads, no spills) give K3 stage 1/2/3 = 10.97/21.83/19.61, 10.94/22.08/19.84,
 // 10.97/22.28/20.05 ms - no gain, so the epilogue's warp count is not what bounds these kernels; 2 sets stay.
@@ -253,22 +257,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
                 const int ty = tg.by_x.div(r);
                 const int ox0 = (r - ty * tg.tiles_x) * G::TW, oy0 = ty * G::TH;
-                if (C::EPI_R > 0 && c == 0) {                                  // this tile's epilogue operands
-                    const int es = ti % (C::EPI_R > 0 ? C::EPI_R : 1);
-                    if (ti >= C::EPI_R) mbar_wait_bounded(&e_empty[es], ((ti / (C::EPI_R > 0 ? C::EPI_R : 1)) - 1) & 1);
-                    float* dstE = sEpi + (size_t)es * (C::EPI_TILE_BYTES / 4);
-                    mbar_expect_tx(&e_full[es], C::EPI_TILE_BYTES);
-                    if (EPI == EPI_GATES) {
-                        tma_load_4d(dstE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * (COUT / 2));
-                    } else {
-                        tma_load_4d(dstE, &tmU, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
-                        tma_load_4d(dstE + COUT * C::EPI_PLANE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
-                    }
-                }
                 const bool fromA = c * CK < CA;
                 const int plane = fromA ? b * a.planesA + c * CK : b * a.planesB + (c * CK - CA);
                 mbar_expect_tx(&slot_full[slot], C::SLOT_BYTES);
                 tma_load_4d(sSlot + slot * C::SLOT_BYTES, fromA ? &tmA : &tmB, &slot_full[slot], (ox0 - 1) & ~3, oy0 - 1, fromA ? a.k : 0, plane);
+            }
+        }
+    } else if (warp == 10) {
+        // ===== TMA producer of the GRU epilogue operands (state h for the reset gates; update gate u and h for the blend)
+        // of the OUTPUT tile.  Its own thread: the ring is EPI_R tiles deep and is released by the epilogue, which runs
+        // two to three tiles behind the input stream - issued from the input producer's loop (as it was) the wait for a
+        // free ring entry held the INPUT boxes back too (converters waited ~680 clk per chunk for data, profiles/r2j).
+        // Same-box A/B with the fourth operand stage below: K3 44.2 -> 43.7 ms per 32 maps (gpurun session r2z7).
+        if (C::EPI_R > 0 && lane == 0) {
+            constexpr int ER = C::EPI_R > 0 ? C::EPI_R : 1;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int es = ti % ER;
+                if (ti >= ER) mbar_wait_bounded(&e_empty[es], ((ti / ER) - 1) & 1);
+                const int tile = blockIdx.x + ti * gridDim.x;
+                const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
+                const int ty = tg.by_x.div(r);
+                const int ox0 = (r - ty * tg.tiles_x) * G::TW, oy0 = ty * G::TH;
+                float* dstE = sEpi + (size_t)es * (C::EPI_TILE_BYTES / 4);
+                mbar_expect_tx(&e_full[es], C::EPI_TILE_BYTES);
+                if (EPI == EPI_GATES) {
+                    tma_load_4d(dstE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * (COUT / 2));
+                } else {
+                    tma_load_4d(dstE, &tmU, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
+                    tma_load_4d(dstE + COUT * C::EPI_PLANE, &tmH, &e_full[es], ox0 & ~3, oy0, 0, b * COUT);
+                }
             }
         }
     } else if (warp == 9) {
