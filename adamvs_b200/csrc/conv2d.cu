@@ -27,7 +27,7 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st, bool tma_only = f
             using T = TcLayer<CA, CB, 24, EPI_BIAS>;
             ConvArgs h = a;
             h.wpk_cout = 48; h.out_cout = 48;
-            ConvPlan p;
+            ConvPlan p{};
             if (T::plan(p, h, N, 1)) {
                 for (int half = 0; half < 2; ++half) {
                     p.args.co_off = 24 * half;
@@ -41,7 +41,7 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st, bool tma_only = f
     if constexpr (STRIDE == 1 && COUT <= 32) {
         if (tc_allowed && aligned && a.win % 4 == 0 && (long long)N * a.hout * a.wout >= 30000) {
             using T = TcLayer<CA, CB, COUT, EPI_BIAS>;
-            ConvPlan p;
+            ConvPlan p{};
             if (T::plan(p, a, N, 1)) {
                 cudaError_t e = T::launch(p, N, PREC_FP32X3, st);
                 return e == cudaSuccess ? 0 : (int)e;
@@ -49,7 +49,7 @@ static int run_conv(const ConvArgs& a, int N, cudaStream_t st, bool tma_only = f
         }
     }
     if (aligned && a.win % 4 == 0 && a.wout % 4 == 0) {
-        ConvPlan p;
+        ConvPlan p{};
         if (L::plan(p, a, N, 1)) {
             cudaError_t e = L::launch(p, N, st);
             return e == cudaSuccess ? 0 : (int)e;

@@ -248,7 +248,11 @@ struct FastDiv {
     }
     __device__ __forceinline__ int div(int n) const { return (int)(((unsigned long long)(unsigned)n * mul) >> shift); }
 };
-struct TileGrid { int tiles_x, tiles_y, ntiles; FastDiv by_x, by_item; };   // ntiles = tiles_x * tiles_y * B; divisors tiles_x, tiles_x * tiles_y
+struct TileGrid {            // ntiles = tiles_x * tiles_y * B; divisors tiles_x, tiles_x * tiles_y
+    int tiles_x, tiles_y, ntiles; FastDiv by_x, by_item;
+    int flip;                // 1: walk the tiles from the last to the first (see regnet_sweep: consecutive kernels of the chain alternate)
+    __device__ __forceinline__ int at(int i) const { return flip ? ntiles - 1 - i : i; }
+};
 
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI, int TH, int PY, int KSPLIT, int CKT, int NSTAGE>
 __global__ void __launch_bounds__(V2Cfg<CA, CB, COUT, COB, STRIDE, TH, PY, KSPLIT, CKT, NSTAGE>::NT)
@@ -288,7 +292,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     auto issue = [&](int g) {                                        // elected thread only
         const int ti = g / G::NSTEP, step = g - ti * G::NSTEP;
-        const int tile = blockIdx.x + ti * gridDim.x;
+        const int tile = tg.at(blockIdx.x + ti * gridDim.x);
         const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
         const int tyq = tg.by_x.div(r);
         const int ox0 = (r - tyq * tg.tiles_x) * TW, oy0 = tyq * TH;
@@ -419,7 +423,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
 
         // -------------------------------------------------------------- epilogue (float4 along x)
-        const int tile = blockIdx.x + ti * gridDim.x;
+        const int tile = tg.at(blockIdx.x + ti * gridDim.x);
         const int b = tg.by_item.div(tile), rr = tile - b * tiles_per_item;
         const int tyq = tg.by_x.div(rr);
         const int ox0 = (rr - tyq * tg.tiles_x) * TW, oy0 = tyq * TH;

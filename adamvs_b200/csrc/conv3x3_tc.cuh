@@ -253,7 +253,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int slot = g % C::NSLOT;
                 if (g >= C::NSLOT) mbar_wait_bounded(&slot_empty[slot], ((g / C::NSLOT) - 1) & 1);
                 const int ti = g / C::NCH, c = g - ti * C::NCH;
-                const int tile = blockIdx.x + ti * gridDim.x;
+                const int tile = tg.at(blockIdx.x + ti * gridDim.x);
                 const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
                 const int ty = tg.by_x.div(r);
                 const int ox0 = (r - ty * tg.tiles_x) * G::TW, oy0 = ty * G::TH;
@@ -274,7 +274,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int es = ti % ER;
                 if (ti >= ER) mbar_wait_bounded(&e_empty[es], ((ti / ER) - 1) & 1);
-                const int tile = blockIdx.x + ti * gridDim.x;
+                const int tile = tg.at(blockIdx.x + ti * gridDim.x);
                 const int b = tg.by_item.div(tile), r = tile - b * tiles_per_item;
                 const int ty = tg.by_x.div(r);
                 const int ox0 = (r - ty * tg.tiles_x) * G::TW, oy0 = ty * G::TH;
@@ -337,7 +337,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int g = 0; g < total; ++g) {
             const int slot = g % C::NSLOT, st = g % C::NA;
             const int ti = g / C::NCH;
-            const int tile = blockIdx.x + ti * gridDim.x;
+            const int tile = tg.at(blockIdx.x + ti * gridDim.x);
             const int rr = tile - tg.by_item.div(tile) * tiles_per_item;
             const int ox0 = (rr - tg.by_x.div(rr) * tg.tiles_x) * G::TW;
             const int off = (ox0 - 1) - ((ox0 - 1) & ~3);                     // column of position 0 inside the box
@@ -390,7 +390,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int acc = ti & 1;
-            const int tile = blockIdx.x + ti * gridDim.x;
+            const int tile = tg.at(blockIdx.x + ti * gridDim.x);
             const int b = tg.by_item.div(tile), rr = tile - b * tiles_per_item;
             const int ty = tg.by_x.div(rr);
             const int ox = (rr - ty * tg.tiles_x) * G::TW + lane, oy0 = ty * G::TH + quarter;

@@ -138,7 +138,7 @@ static cudaError_t launch_upconv(const float* inA, const float* inB, const float
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
 struct Layer {
     using L = ConvLayer<CA, CB, COUT, COB, STRIDE, EPI>;
-    ConvPlan plan;
+    ConvPlan plan{};
     ConvArgs args;
     bool tma = false;
     void setup(const ConvArgs& a, int B, int depthA) {

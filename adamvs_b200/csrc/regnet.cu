@@ -249,6 +249,7 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant_
     pdl_wait();                                                    // everything above overlapped the previous kernel's tail
 
     auto origin = [&](int item, int& b, int& ox0, int& oy0) {
+        item = tg.at(item);
         b = tg.by_item.div(item);
         const int t = item - b * (tg.tiles_x * tg.tiles_y);
         const int tyi = tg.by_x.div(t);
@@ -400,7 +401,7 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant_
 
 template <bool UP, int TH>
 static cudaError_t launch_tail_tma(const CUtensorMap& tmH2, const CUtensorMap& tmH1, const float* wpk_up, const float* up_b,
-                                   OutWeights ow, float* logits, int k, int D, int h, int w, int B, cudaStream_t st) {
+                                   OutWeights ow, float* logits, int k, int D, int h, int w, int B, int flip, cudaStream_t st) {
     using G = TailTma<UP, TH>;
     auto kern = tail_tma_kernel<UP, TH>;
     static bool ready[64] = {false};
@@ -418,6 +419,7 @@ static cudaError_t launch_tail_tma(const CUtensorMap& tmH2, const CUtensorMap& t
     tg.ntiles = tg.tiles_x * tg.tiles_y * B;
     if (tg.ntiles >= (1 << 26)) return cudaErrorInvalidValue;
     tg.by_x = FastDiv(tg.tiles_x); tg.by_item = FastDiv(tg.tiles_x * tg.tiles_y);
+    tg.flip = flip;
     int ctas = 2 * sm_count();
     if (ctas > tg.ntiles) ctas = tg.ntiles;
     return launch_pdl(kern, dim3(ctas), dim3(256), G::SMEM, st, tmH2, tmH1, wpk_up, up_b, ow, logits, k, D, h, w, tg);
@@ -694,7 +696,7 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
 
     // TMA needs 16-byte global row strides at both resolutions
     bool tma = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(volume) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0);
-    ConvPlan p1, p2, p3, p4, p5, p6;
+    ConvPlan p1{}, p2{}, p3{}, p4{}, p5{}, p6{};
     if (tma) {
         bool ok = (C == 8 ? Conv1<8>::plan(p1, a1, B, D) : C == 16 ? Conv1<16>::plan(p1, a1, B, D) : Conv1<32>::plan(p1, a1, B, D));
         ok = ok && Gates1::plan(p2, a2, B, 1) && Cand1::plan(p3, a3, B, 1) && Conv2::plan(p4, a4, B, 1)
@@ -710,7 +712,7 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
     const bool auto_tc = tma && math_mode == ADAMVS_MATH_AUTO;
     const bool tc_full = all_tc || (auto_tc && px >= 30000), tc_half = all_tc || (auto_tc && px / 4 >= 30000);
     const bool tc1 = tc_full, tc2 = tc_full, tc3 = tc_full, tc5 = tc_half, tc6 = tc_half;
-    ConvPlan q1, q2, q3, q5, q6;
+    ConvPlan q1{}, q2{}, q3{}, q5{}, q6{};
     {
         bool ok = true;
         if (tc1) ok = ok && (C == 8 ? TcConv1<8>::plan(q1, a1, B, D) : C == 16 ? TcConv1<16>::plan(q1, a1, B, D) : TcConv1<32>::plan(q1, a1, B, D));
@@ -743,8 +745,19 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
         }
     }
 
+    // Tile order of consecutive kernels alternates (first-to-last, last-to-first, ...): a persistent kernel leaves the END
+    // of the tensor it wrote in the L2; its consumer starts there.  ADAMVS_K3_ZIGZAG=0 switches it off (measurement hook).
+    static const bool zigzag = [] { const char* e = getenv("ADAMVS_K3_ZIGZAG"); return !(e && *e == '0'); }();
+    int launches = 0;
+    auto zz = [&]() { return zigzag ? (launches++ & 1) : 0; };
     for (int k = 0; k < D; ++k) {
         if (tma) {
+            p1.tg.flip = q1.tg.flip = zz();
+            p2.tg.flip = q2.tg.flip = zz();
+            p3.tg.flip = q3.tg.flip = zz();
+            p4.tg.flip = zz();
+            p5.tg.flip = q5.tg.flip = zz();
+            p6.tg.flip = q6.tg.flip = zz();
             if (tc1) {
                 q1.args.k = k;
                 if (C == 8) ADAMVS_TRY(TcConv1<8>::launch(q1, B, prec, st));
@@ -774,10 +787,10 @@ static int regnet_sweep(const float* volume, const adamvs_regnet_weights* hwts, 
         }
         // 7+8: up1 + skip + relu -> output layer -> logits[:, k], one launch
         if (tail_th == 24) {
-            ADAMVS_TRY((launch_tail_tma<true, 24>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
+            ADAMVS_TRY((launch_tail_tma<true, 24>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, zz(), st)));
         } else if (tail_th == 16) {
-            if (out_up) ADAMVS_TRY((launch_tail_tma<true, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
-            else ADAMVS_TRY((launch_tail_tma<false, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, st)));
+            if (out_up) ADAMVS_TRY((launch_tail_tma<true, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, zz(), st)));
+            else ADAMVS_TRY((launch_tail_tma<false, 16>(tmH2, tmH1, ws.pk_up1, hwts->up1_b, ow, logits, k, D, h, w, B, zz(), st)));
         } else {
             dim3 grid(((w + kTailW - 1) / kTailW) * ((h + kTailH - 1) / kTailH), 1, B);
             if (out_up) ADAMVS_TRY(launch_pdl(tail_regress_kernel<true>, grid, dim3(256), 0, st, (const float*)ws.h2, (const float*)ws.pk_up1, hwts->up1_b, (const float*)ws.h1, ow, logits, k, D, h, w));
