@@ -69,7 +69,7 @@ class Workload:
 
 
 WORKLOADS = {
-    "config1": Workload("config1", 384, 768, (48, 32, 8), 192, "adamvs", 32,
+    "config1": Workload("config1", 384, 768, (48, 32, 8), 192, "adamvs", 64,
                         "configs[1]: Ada-MVS 5-view (1 ref + 4 src) 768x384 cascade inference, fp32, random-init weights; "
                         "reference views are independent and are sharded over ranks (configs[2])"),
     "config4": Workload("config4", 1536, 1536, (96, 32, 8), 192, "adamvs", 4,
@@ -518,6 +518,7 @@ def main():
         try:
             with open(traffic_file) as fh:
                 t = json.load(fh)
+            t = t.get(str(B), t)                                   # one ncu capture per bench batch
             if int(t.get("batch", -1)) == B:
                 roofline["traffic"] = t.get("dram_bytes_per_launch")
                 roofline["traffic_source"] = t.get("source")
