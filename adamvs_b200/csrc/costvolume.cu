@@ -177,7 +177,12 @@ static int launch_fused_volume(const float* feat, const float* relproj, const Hy
 // latency-bound: 4.58/7.47/5.44 ms.  G = 2 ships.
 // The same box serves 4*G planes and is 32 texels wide: L2 -> shared-memory traffic per output is half of round 1's.
 // ================================================================================================
-constexpr int kBW = 32, kBH = 12;          // source box per (view, channel): pitch = the 32 banks
+// Source box per (view, channel).  48 columns, not 32: the box is also the shared-memory pitch (TMA writes dense rows), and
+// the two planes (half-warps) of a warp usually sample adjacent source ROWS at almost the same columns - with a pitch of
+// 32 words those are the same banks (a 2-way conflict on most loads), with 48 they are 16 banks apart.  Same-box A/B at
+// the bench batch: stage 2 / 3 10.03 / 7.45 -> 9.11 / 6.48 ms, shared wavefronts 2186 M -> 1793 M (conflicts 932 M -> 539 M),
+// profiles/r2zc_* vs r2zf_*.  74 KB of stage buffers per CTA, still two CTAs per SM.
+constexpr int kBW = 48, kBH = 12;
 constexpr int kBox = kBW * kBH;
 constexpr int kCK = 4;                      // channels per pipeline stage
 // Rough depth (an untrained or noisy previous stage, oblique geometry) spreads a tile's footprint over more source
