@@ -394,6 +394,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int b = tg.by_item.div(tile), rr = tile - b * tiles_per_item;
             const int ty = tg.by_x.div(rr);
             const int ox = (rr - ty * tg.tiles_x) * G::TW + lane, oy0 = ty * G::TH + quarter;
+            float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};               // RAW_STATS: this lane's moments of the tile, per channel half
             auto process = [&](int sI) {
                 const int gi = eset + NSET * sI;
                 const int mt = gi / NCG, c0 = (gi - mt * NCG) * CG;
@@ -422,7 +423,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     v[c] += __shfl_down_sync(0xffffffffu, __uint_as_float(rh[2][c]) + __uint_as_float(rl[2][c]), 2);
                 }
                 if (tid == 0 && gi == 0) TC_TRACE(3, ti, 1);
-                if (!valid) return;
+                if (EPI != EPI_RAW_STATS && !valid) return;                   // (RAW_STATS: every lane stays for the warp reduction below)
                 // All values first, all stores afterwards: the operands below come from (generic-address) shared memory,
                 // and the compiler will not move such a load above an earlier global store - with load, MUFU and store
                 // interleaved per channel the eight ~180-clk dependency chains ran one after the other (profiles/r02e).
@@ -440,6 +441,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         res[c] = u * hv + (1.f - u) * tanh_f(v[c] + sBias[co]);
                     } else if (EPI == EPI_RELU) {
                         res[c] = fmaxf(v[c], 0.f);
+                    } else if (EPI == EPI_RAW_STATS) {                         // raw conv + bias; GroupNorm moments below
+                        res[c] = v[c] + sBias[co];
                     } else {                                                   // EPI_BIAS
                         const float y = v[c] + sBias[co];
                         res[c] = a.relu ? fmaxf(y, 0.f) : y;
@@ -449,8 +452,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     float* dst;
                     if (EPI == EPI_GATES) dst = c0 < HC ? a.out0 + ((size_t)b * HC + c0) * plane + pix : a.out1 + ((size_t)b * HC + (c0 - HC)) * plane + pix;
                     else dst = a.out0 + ((size_t)b * ocout + a.co_off + c0) * plane + pix;
+                    if (EPI == EPI_RAW_STATS) {
+                        float s = 0.f, q = 0.f;
+                        if (valid) {
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) dst[(size_t)c * plane] = res[c];
+                            for (int c = 0; c < CG; ++c) { dst[(size_t)c * plane] = res[c]; s += res[c]; q = fmaf(res[c], res[c], q); }
+                        }
+                        const bool upper = a.stats_split && (a.co_off + c0) >= ocout / 2;       // warp-uniform
+                        st_s[0] += upper ? 0.f : s; st_q[0] += upper ? 0.f : q;
+                        st_s[1] += upper ? s : 0.f; st_q[1] += upper ? q : 0.f;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) dst[(size_t)c * plane] = res[c];
+                    }
                 }
                 if (tid == 0 && gi == 0) TC_TRACE(3, ti, 2);
             };
@@ -462,6 +476,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int sI = 0; sI < NGW; ++sI)
                 if (eset + NSET * sI < NG) process(sI);                        // steps eset, eset + NSET, ... of this warp set
+            if (EPI == EPI_RAW_STATS) {
+                // per-item moments of the raw output for the one-group GroupNorm that follows (msrednet.cu): warp partials
+                // in fp64 -> atomics on stats[b][half][sum, sum of squares], like the FFMA kernels' EPI_RAW_STATS
+#pragma unroll
+                for (int gpart = 0; gpart < 2; ++gpart) {
+                    double ds = (double)st_s[gpart], dq = (double)st_q[gpart];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
+                    if (lane == 0 && (gpart == 0 || a.stats_split)) {
+                        atomicAdd(a.stats + ((size_t)b * 2 + gpart) * 2, ds);
+                        atomicAdd(a.stats + ((size_t)b * 2 + gpart) * 2 + 1, dq);
+                    }
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -20,6 +20,8 @@
 // applies normalisation, activation and the GRU blend.  All statistics buffers of a sweep are zeroed
 // once up front, so the plane loop contains kernel launches only.
 #include "conv3x3.cuh"
+#include "conv3x3_tc.cuh"
+#include <string.h>
 #include "regress_fused.cuh"
 
 namespace adamvs {
@@ -134,21 +136,57 @@ static cudaError_t launch_upconv(const float* inA, const float* inB, const float
     return cudaGetLastError();
 }
 
-// ---- one conv layer with both launch paths (TMA persistent / generic tiles) ----------------------------
+// ---- one conv layer with its launch paths (tensor cores / TMA persistent FFMA / generic tiles) -------------
+// Round 2: the GRU convolutions of the levels whose weights fit the tensor-core kernel's shared memory (levels 1-3:
+// 8/16/32 hidden channels) run on conv3x3_tc.cuh like Ada-MVS's regulariser - same hi/lo tf32 split, fp32 accuracy -
+// with an EPI_RAW_STATS epilogue (raw output + bias, GroupNorm moments as fp64 atomics).  A 64-channel gate
+// convolution (N = 3 x 2 x 64 exceeds one MMA) runs as two 32-channel slices.  Planes below ~2 tiles per SM and level 4
+// (128 input channels: 295 KB of split weights) keep the FFMA kernels.  ADAMVS_K3_MATH=ffma|tc forces one path (tests).
+static int msred_math() {
+    static const int m = [] {
+        const char* e = getenv("ADAMVS_K3_MATH");
+        return (e && !strcmp(e, "ffma")) ? 0 : (e && !strcmp(e, "tc")) ? 2 : 1;      // 0 FFMA, 1 auto, 2 tensor cores wherever possible
+    }();
+    return m;
+}
+
 template <int CA, int CB, int COUT, int COB, int STRIDE, int EPI>
 struct Layer {
     using L = ConvLayer<CA, CB, COUT, COB, STRIDE, EPI>;
-    ConvPlan plan{};
+    static constexpr bool TC_OK = STRIDE == 1 && EPI == EPI_RAW_STATS && CA + CB <= 64 && COUT <= 64;
+    static constexpr int TC_COUT = COUT > 32 ? 32 : COUT;          // slice width
+    using T = TcLayer<CA, CB, TC_OK ? TC_COUT : 8, TC_OK ? EPI : EPI_RELU>;
+    ConvPlan plan{}, tplan{};
     ConvArgs args;
-    bool tma = false;
+    bool tma = false, tc = false;
     void setup(const ConvArgs& a, int B, int depthA) {
         args = a;
         const bool aligned = ((reinterpret_cast<uintptr_t>(a.inA) | reinterpret_cast<uintptr_t>(a.inB) |
                                reinterpret_cast<uintptr_t>(a.out0) | reinterpret_cast<uintptr_t>(a.out1) |
                                reinterpret_cast<uintptr_t>(a.hstate) | reinterpret_cast<uintptr_t>(a.ugate)) % 16) == 0;
         tma = aligned && (a.win % 4 == 0) && (a.wout % 4 == 0) && L::plan(plan, a, B, depthA);
+        if constexpr (TC_OK) {
+            const long long px = (long long)a.hout * a.wout * B;
+            if (tma && msred_math() != 0 && (msred_math() == 2 || px >= 30000)) {
+                ConvArgs t = a;
+                if (TC_COUT != COUT) { t.wpk_cout = COUT; t.out_cout = COUT; }
+                tc = T::plan(tplan, t, B, depthA);
+            }
+        }
     }
+    void set_stats(double* p) { args.stats = p; plan.args.stats = p; tplan.args.stats = p; }
     cudaError_t run(int B, int k, cudaStream_t st) {
+        if constexpr (TC_OK) {
+            if (tc) {
+                tplan.args.k = k;
+                for (int co = 0; co < COUT; co += TC_COUT) {
+                    tplan.args.co_off = co;
+                    cudaError_t e = T::launch(tplan, B, PREC_FP32X3, st);
+                    if (e != cudaSuccess) return e;
+                }
+                return cudaSuccess;
+            }
+        }
         if (tma) { plan.args.k = k; return L::launch(plan, B, st); }
         ConvArgs a = args;
         a.inA = args.inA + (size_t)k * args.hin * args.win;        // plane k of a [.., D, h, w] volume (k = 0 otherwise)
@@ -274,8 +312,8 @@ static int run_msred(const float* volume, const adamvs_msred_weights* wts, const
     auto gru = [&](auto& Lg, auto& Lo, int l, int k, int kvol) -> int {
         double* sg = ws.stats + ((size_t)k * 8 + 2 * l) * B * 4;
         double* so = ws.stats + ((size_t)k * 8 + 2 * l + 1) * B * 4;
-        Lg.args.stats = sg; Lg.plan.args.stats = sg;
-        Lo.args.stats = so; Lo.plan.args.stats = so;
+        Lg.set_stats(sg);
+        Lo.set_stats(so);
         ADAMVS_TRY(Lg.run(B, kvol, st));
         const int hw4 = (int)px[l];
         dim3 grid((hw4 + 255) / 256, hc[l], B);

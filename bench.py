@@ -493,7 +493,7 @@ def main():
                           "frac_of_ffma_peak": fl / st["ms_mean"] * 1e-9 / ffma_peak,
                           "frac_of_bf16_tensor_peak": fl / st["ms_mean"] * 1e-9 / tensor_peak})
             if msred:
-                entry["bound"] = "fp32 FFMA (GroupNorm conv-GRU on the FFMA kernels)"
+                entry["bound"] = "tensor + FFMA (GroupNorm conv-GRU: GRU convs of levels 1-3 on tcgen05 kind::tf32 with the hi/lo split, level 4, strided and transposed convs on FFMA)"
             else:
                 # fp32 accuracy on kind::tf32: A_hi W_hi + A_hi W_lo + A_lo W_hi = 3 tf32 products per fp32 product
                 # (the 8-channel layers' second pass is padded from N = 24 to 32, not counted);

@@ -598,6 +598,23 @@ def test_conv_tile_configurations_forced(cfg):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
+@pytest.mark.parametrize("math", ["tc", "ffma"])
+def test_msred_regulariser_math_paths_forced(math):
+    """MS-REDNet's GRU convolutions of levels 1-3 run on the tensor-core kernel (EPI_RAW_STATS epilogue: raw output +
+    GroupNorm moments) when a plane has >= 30 k pixels, which the CPU oracle cannot check in seconds: both paths are
+    forced (ADAMVS_K3_MATH) in a fresh process and the K6 kernel test and the whole MS-REDNet forwards re-run."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ADAMVS_K3_MATH=math)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_regnet_msred_vs_oracle or test_msred_forward_matches_reference_golden or test_msred_forward_full_size_vs_oracle"],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout, r.stdout[-500:]
+
+
 @pytest.mark.parametrize("var,cfg", [("ADAMVS_TAIL_CFG", "0"), ("ADAMVS_TAIL_CFG", "16"), ("ADAMVS_TAIL_CFG", "24"), ("ADAMVS_DECONV_CFG", "0")])
 def test_tail_and_transposed_conv_variants_forced(var, cfg):
     """The regulariser's tail picks the plain kernel (rows TMA cannot address), or the TMA-fed one with 32x16 or 32x24
